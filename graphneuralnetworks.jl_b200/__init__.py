@@ -1,0 +1,17 @@
+"""graphneuralnetworks.jl_b200 — B200-native (sm_100a) message-passing engine behind GNNlib.jl's
+`propagate` / `apply_edges` / `aggregate_neighbors` API.
+
+Import name: ``gnnb200`` (the directory name contains a dot, so the repo-root shim ``gnnb200.py`` loads this
+package under that name).  Product code = csrc/ (CUDA kernels + C ABI, built into lib/libgnnb200.so) and the
+host-side mirror of the reference interface in this package.  Nothing here imports ``oracle/``.
+"""
+from . import _lib
+from ._lib import GNNBError, device_count, launch_count, version
+from .graph import (GNNGraph, add_self_loops, batch, colmajor, degree, edge_index, get_edge_weight,
+                    graph_indicator, jl_randn, jl_zeros, rmat_graph, rows, set_edge_weight, unrows)
+from .msgpass import (Fix1, aggregate_neighbors, apply_edges, check_num_edges, check_num_nodes, copy_xi, copy_xj,
+                      e_mul_xj, expand_srcdst, mean, propagate, softmax_edge_neighbors, w_mul_xj, xi_dot_xj,
+                      xi_sub_xj, xj_sub_xi)
+from .layers import (GATConv, GCNConv, SAGEConv, gat_conv, gat_message, gcn_conv, identity, relu, sage_conv)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

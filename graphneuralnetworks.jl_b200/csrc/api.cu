@@ -1,0 +1,224 @@
+// api.cu — C-ABI glue: error state, propagate / pullbacks / GCN core / host-buffer entries / RMAT.
+#include "common.cuh"
+#include <string.h>
+#include <math_constants.h>
+
+namespace gnnb {
+
+static thread_local char t_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+int edge_dot(gnnb_graph* g, const float* dout, const float* x, const float* cs, const float* ct, int64_t D,
+             float* dw_coo, cudaStream_t st);
+int maxmin_bwd(gnnb_graph* g, const float* w_plan_src, const float* x, const float* dout, const float* out_fwd,
+               int64_t D, float* dx, cudaStream_t st);
+
+__global__ void mul_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ o) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] * b[i];
+}
+
+// ---- RMAT (Graph500 a,b,c,d = .57,.19,.19,.05), counter-based, integer thresholds ------------------
+__host__ __device__ static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void rmat_kernel(int64_t N, int64_t E, uint64_t seed, int scale, int64_t* __restrict__ src,
+                            int64_t* __restrict__ dst) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= E) return;
+    const uint32_t TA = 9563013u, TB = 12750684u, TC = 15938355u;  // floor(.57, .76, .95 * 2^24)
+    uint64_t s = 0, d = 0;
+    for (uint64_t retry = 0;; ++retry) {
+        uint64_t state = splitmix64(seed ^ splitmix64((uint64_t)id * 0x100000001B3ull + retry));
+        s = 0; d = 0;
+        for (int l = 0; l < scale; ++l) {
+            state = splitmix64(state);
+            const uint32_t u = (uint32_t)(state >> 40);
+            const uint64_t sb = (u >= TB) ? 1 : 0;                       // quadrants c,d set the source bit
+            const uint64_t db = (u >= TA && u < TB) || (u >= TC) ? 1 : 0;  // quadrants b,d set the target bit
+            s = (s << 1) | sb;
+            d = (d << 1) | db;
+        }
+        if ((int64_t)s < N && (int64_t)d < N) break;
+        if (retry >= 63) { s %= (uint64_t)N; d %= (uint64_t)N; break; }
+    }
+    src[id] = (int64_t)s + 1;
+    dst[id] = (int64_t)d + 1;
+}
+
+}  // namespace gnnb
+
+using namespace gnnb;
+static inline unsigned nblk(int64_t n) { return (unsigned)ceil_div(n, 256); }
+
+static int check_common(gnnb_graph_t g, int msg, int aggr, int64_t D, const float* w) {
+    if (!g) GNNB_FAIL(GNNB_EINVAL, "graph handle is NULL");
+    if (msg != GNNB_COPY_XJ && msg != GNNB_W_MUL_XJ) GNNB_FAIL(GNNB_EINVAL, "unknown message function %d", msg);
+    if (aggr < GNNB_SUM || aggr > GNNB_MIN) GNNB_FAIL(GNNB_EINVAL, "unknown aggregation %d", aggr);
+    if (D <= 0) GNNB_FAIL(GNNB_ESIZE, "feature dimension must be positive (got %lld)", (long long)D);
+    if (msg == GNNB_W_MUL_XJ && !w) GNNB_FAIL(GNNB_EINVAL, "w_mul_xj/e_mul_xj needs the edge weights");
+    return GNNB_OK;
+}
+
+// weights in COO order -> plan order of `c` (into ws2); returns nullptr when there are none
+static int plan_weights(gnnb_graph* g, const Csr& c, int msg, const float* w, size_t ws2_off_floats, const float** out,
+                        cudaStream_t st) {
+    *out = nullptr;
+    if (msg != GNNB_W_MUL_XJ || !w || g->E == 0) return GNNB_OK;
+    GNNB_TRY(ensure_ws2(g, sizeof(float) * ((size_t)g->E + ws2_off_floats)));
+    float* p = g->ws2 + ws2_off_floats;
+    GNNB_TRY(permute_edge_values(c, g->E, w, 1, p, st));
+    *out = p;
+    return GNNB_OK;
+}
+
+extern "C" {
+
+const char* gnnb_last_error(void) { return t_err; }
+const char* gnnb_version(void) { return "gnnb200 0.1 sm_100a"; }
+int gnnb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int64_t gnnb_launch_count(void) { return g_launches.load(); }
+
+int gnnb_propagate(gnnb_graph_t g, int transposed, int msg, int aggr, const float* x, const float* w,
+                   const float* cs, const float* ct, int64_t D, float* out, void* stream) {
+    GNNB_TRY(check_common(g, msg, aggr, D, w));
+    if (!x || !out) GNNB_FAIL(GNNB_EINVAL, "x/out is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNB_TRY(ensure_csr(g, transposed != 0, st));
+    const Csr& c = transposed ? g->by_src : g->by_dst;
+    SegArgs a;
+    a.x = x; a.cs = cs; a.ct = ct; a.out = out; a.D = D; a.aggr = aggr;
+    GNNB_TRY(plan_weights(g, c, msg, w, 0, &a.w, st));
+    return seg_reduce(g, c, a, st);
+}
+
+int gnnb_propagate_bwd(gnnb_graph_t g, int msg, int aggr, const float* dout, const float* x, const float* w,
+                       const float* cs, const float* ct, const float* out_fwd, int64_t D, float* dx, float* dw,
+                       void* stream) {
+    GNNB_TRY(check_common(g, msg, aggr, D, w));
+    if (!dout) GNNB_FAIL(GNNB_EINVAL, "dout is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool ismax = aggr == GNNB_MAX || aggr == GNNB_MIN;
+    if (ismax) {
+        if (dw) GNNB_FAIL(GNNB_EUNSUPPORTED, "dw for max/min aggregation is not implemented");
+        if (cs || ct) GNNB_FAIL(GNNB_EUNSUPPORTED, "max/min pullback with node scales is not implemented");
+        if (!x || !out_fwd) GNNB_FAIL(GNNB_EINVAL, "max/min pullback needs x and the forward output");
+        if (!dx) return GNNB_OK;
+        GNNB_TRY(ensure_csr(g, true, st));
+        const float* wp = nullptr;
+        GNNB_TRY(plan_weights(g, g->by_src, msg, w, 0, &wp, st));
+        return maxmin_bwd(g, wp, x, dout, out_fwd, D, dx, st);
+    }
+    // scale of the gathered dout row: ct (SUM) or ct/deg (MEAN)
+    const float* gscale = ct;
+    size_t off = 0;
+    if (aggr == GNNB_MEAN) {
+        GNNB_TRY(ensure_invdeg(g, g->by_dst, st));
+        if (ct) {
+            GNNB_TRY(ensure_ws2(g, sizeof(float) * ((size_t)g->n_dst + (size_t)g->E)));
+            if (g->n_dst > 0) {
+                mul_vec_kernel<<<nblk(g->n_dst), 256, 0, st>>>(ct, g->by_dst.invdeg, g->n_dst, g->ws2);
+                GNNB_LAUNCHED();
+            }
+            gscale = g->ws2;
+            off = (size_t)g->n_dst;
+        } else {
+            gscale = g->by_dst.invdeg;
+        }
+    }
+    if (dx) {
+        GNNB_TRY(ensure_csr(g, true, st));
+        SegArgs a;
+        a.x = dout; a.cs = gscale; a.ct = cs; a.out = dx; a.D = D; a.aggr = GNNB_SUM;
+        GNNB_TRY(plan_weights(g, g->by_src, msg, w, off, &a.w, st));
+        GNNB_TRY(seg_reduce(g, g->by_src, a, st));
+    }
+    if (dw) {
+        if (msg != GNNB_W_MUL_XJ) GNNB_FAIL(GNNB_EINVAL, "dw requested for a message without weights");
+        if (!x) GNNB_FAIL(GNNB_EINVAL, "dw needs x");
+        GNNB_TRY(edge_dot(g, dout, x, cs, gscale, D, dw, st));
+    }
+    return GNNB_OK;
+}
+
+int gnnb_gcn_propagate(gnnb_graph_t g, int transposed, const float* x, const float* w, const float* c,
+                       int64_t D, float* out, void* stream) {
+    if (!g) GNNB_FAIL(GNNB_EINVAL, "graph handle is NULL");
+    if (g->n_src != g->n_dst) GNNB_FAIL(GNNB_ESIZE, "gcn_propagate needs num_src == num_dst");
+    if (!c) GNNB_FAIL(GNNB_EINVAL, "c (from gnnb_gcn_norm) is NULL");
+    return gnnb_propagate(g, transposed, w ? GNNB_W_MUL_XJ : GNNB_COPY_XJ, GNNB_SUM, x, w, c, c, D, out, stream);
+}
+
+// ---- host-buffer entries ------------------------------------------------------------------------
+static int host_pass(gnnb_graph_t g, int transposed, int msg, int aggr, int gcn, const float* x_host,
+                     const float* w_host, int64_t D, float* out_host) {
+    if (!g) GNNB_FAIL(GNNB_EINVAL, "graph handle is NULL");
+    if (!x_host || !out_host) GNNB_FAIL(GNNB_EINVAL, "host buffer is NULL");
+    if (D <= 0) GNNB_FAIL(GNNB_ESIZE, "feature dimension must be positive");
+    const int64_t n_in = transposed ? g->n_dst : g->n_src, n_out = transposed ? g->n_src : g->n_dst;
+    float *dx = nullptr, *dout = nullptr, *dw = nullptr, *dc = nullptr;
+    cudaStream_t st = nullptr;
+    int status = GNNB_OK;
+#define HP(expr) { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s: %s", #expr, cudaGetErrorString(_e)); status = (_e == cudaErrorMemoryAllocation) ? GNNB_ENOMEM : GNNB_ECUDA; goto done; } }
+    HP(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HP(cudaMalloc(&dx, sizeof(float) * (size_t)(n_in * D > 0 ? n_in * D : 1)));
+    HP(cudaMalloc(&dout, sizeof(float) * (size_t)(n_out * D > 0 ? n_out * D : 1)));
+    HP(cudaMemcpyAsync(dx, x_host, sizeof(float) * (size_t)(n_in * D), cudaMemcpyHostToDevice, st));
+    if (w_host && g->E > 0) {
+        HP(cudaMalloc(&dw, sizeof(float) * (size_t)g->E));
+        HP(cudaMemcpyAsync(dw, w_host, sizeof(float) * (size_t)g->E, cudaMemcpyHostToDevice, st));
+    }
+    if (gcn) {
+        HP(cudaMalloc(&dc, sizeof(float) * (size_t)(g->n_dst > 0 ? g->n_dst : 1)));
+        if ((status = gnnb_gcn_norm(g, dw, dc, st))) goto done;
+        if ((status = gnnb_gcn_propagate(g, transposed, dx, dw, dc, D, dout, st))) goto done;
+    } else {
+        if ((status = gnnb_propagate(g, transposed, msg, aggr, dx, dw, nullptr, nullptr, D, dout, st))) goto done;
+    }
+    HP(cudaMemcpyAsync(out_host, dout, sizeof(float) * (size_t)(n_out * D), cudaMemcpyDeviceToHost, st));
+    HP(cudaStreamSynchronize(st));
+#undef HP
+done:
+    cudaFree(dx); cudaFree(dout); cudaFree(dw); cudaFree(dc);
+    if (st) cudaStreamDestroy(st);
+    return status;
+}
+
+int gnnb_propagate_host(gnnb_graph_t g, int transposed, int msg, int aggr, const float* x_host,
+                        const float* w_host, int64_t D, float* out_host) {
+    GNNB_TRY(check_common(g, msg, aggr, D, w_host));
+    return host_pass(g, transposed, msg, aggr, 0, x_host, w_host, D, out_host);
+}
+int gnnb_gcn_propagate_host(gnnb_graph_t g, int transposed, const float* x_host, const float* w_host,
+                            int64_t D, float* out_host) {
+    return host_pass(g, transposed, GNNB_COPY_XJ, GNNB_SUM, 1, x_host, w_host, D, out_host);
+}
+
+int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t* src_dev, int64_t* dst_dev,
+                    void* stream) {
+    if (num_nodes <= 0 || num_edges < 0) GNNB_FAIL(GNNB_ESIZE, "rmat: bad sizes");
+    if (!src_dev || !dst_dev) GNNB_FAIL(GNNB_EINVAL, "rmat: NULL output");
+    if (gnnb_device_count() <= 0) GNNB_FAIL(GNNB_ECUDA, "no CUDA device");
+    int scale = 0;
+    while (((int64_t)1 << scale) < num_nodes) ++scale;
+    if (num_edges == 0) return GNNB_OK;
+    rmat_kernel<<<nblk(num_edges), 256, 0, (cudaStream_t)stream>>>(num_nodes, num_edges, seed, scale, src_dev, dst_dev);
+    GNNB_LAUNCHED();
+    return GNNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+"""The three functional layers that ride on the hot path, with the reference's signatures:
+
+    gcn_conv(l, g, x, edge_weight, norm_fn, conv_weight)   GNNlib/src/layers/conv.jl:14-72
+    gat_conv(l, g, x, e)  + gat_message                    GNNlib/src/layers/conv.jl:112-167
+    sage_conv(l, g, x)                                     GNNlib/src/layers/conv.jl:277-283
+
+``l`` is duck-typed exactly as in the reference (a Flux struct or a Lux NamedTuple there; any object with the
+same field names here): GCN ``weight, bias, σ|sigma, add_self_loops, use_edge_weight``; GAT ``dense_x, dense_e, a,
+bias, σ, negative_slope, channel, heads, concat, add_self_loops, dropout``; SAGE ``weight, bias, σ, aggr``.
+``GCNConv`` / ``GATConv`` / ``SAGEConv`` are thin parameter holders mirroring the Flux constructors
+(GraphNeuralNetworks/src/layers/conv.jl:77-104, 309-346, 770-787).
+
+Arrays are Julia-shaped and column-major: x is (Din, N), weight is (Dout, Din), GAT's ``a`` is (2C, H).
+The dense contractions (W*x) go to cuBLAS sgemm (fp32, no TF32) — a plain library GEMM, as in the reference.
+"""
+from __future__ import annotations
+
+import math
+import operator
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib
+from .graph import GNNGraph, _stream, add_self_loops, degree, rows, unrows
+from .msgpass import (Fix1, _GCNPropagateFn, _f32, aggregate_neighbors, apply_edges, check_num_nodes, copy_xj,
+                      e_mul_xj, expand_srcdst, mean, propagate, softmax_edge_neighbors, w_mul_xj)
+
+
+def identity(x):
+    return x
+
+
+def relu(x):
+    return torch.relu(x)
+
+
+def _sigma(l) -> Callable:
+    for name in ("σ", "sigma", "activation"):
+        if hasattr(l, name):
+            return getattr(l, name)
+    return identity
+
+
+def _bias(l):
+    b = getattr(l, "bias", None)
+    if b is None or b is False:
+        return None
+    return b
+
+
+def _matmul(W: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Julia `W * x` for W (Dout, Din), x (Din, N) column-major -> (Dout, N) column-major (rows @ W^T)."""
+    return unrows(rows(x) @ W.t())
+
+
+def _add_bias(x: torch.Tensor, b) -> torch.Tensor:
+    if b is None:
+        return x
+    return x + b.reshape(-1, 1)
+
+
+def default_norm_fn(d: torch.Tensor) -> torch.Tensor:
+    """d -> 1 ./ sqrt.(d) — GraphNeuralNetworks/src/layers/conv.jl:99."""
+    return 1.0 / torch.sqrt(d)
+
+
+# ------------------------------------------------------------------------------------------- GCNConv
+def check_gcnconv_input(g: GNNGraph, edge_weight) -> None:
+    """GNNlib/src/layers/conv.jl:3-12."""
+    if edge_weight is not None and edge_weight.numel() != g.num_edges:
+        raise ValueError(f"Wrong number of edge weights (expected {g.num_edges} but given {edge_weight.numel()})")
+
+
+def _gcn_c(g: GNNGraph) -> torch.Tensor:
+    """c = 1 ./ sqrt.(degree(g; dir=:in, edge_weight=false)) on the device, cached on the (immutable) graph."""
+    c = getattr(g, "_gcn_c_cache", None)
+    if c is None:
+        p = g.plan()
+        c = torch.empty(g.num_nodes, dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib.check(lib.gnnb_gcn_norm(p.h, None, c.data_ptr(), _stream(p.device)))
+        g._gcn_c_cache = c
+    return c
+
+
+def gcn_conv(l, g: GNNGraph, x: torch.Tensor, edge_weight: Optional[torch.Tensor] = None,
+             norm_fn: Optional[Callable] = None, conv_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:14-72, statement for statement; the unweighted default-norm case runs the
+    fused kernel (degree from rowptr, both 1/sqrt(d) scalings folded into the load/store of one pass)."""
+    check_gcnconv_input(g, edge_weight)
+    if conv_weight is None:
+        weight = l.weight
+    else:
+        weight = conv_weight
+        if tuple(weight.shape) != tuple(l.weight.shape):
+            raise ValueError(f"The weight matrix has the wrong size. Expected {tuple(l.weight.shape)} "
+                             f"but got {tuple(weight.shape)}")
+    if l.add_self_loops:
+        g = add_self_loops(g)
+        if edge_weight is not None:
+            edge_weight = torch.cat([edge_weight, torch.ones(g.num_nodes, dtype=edge_weight.dtype,
+                                                             device=edge_weight.device)])
+            assert edge_weight.numel() == g.num_edges
+    Dout, Din = weight.shape
+    if Dout < Din:
+        x = _matmul(weight, x)  # multiply before convolution if it is more convenient
+    xj, xi = expand_srcdst(g, x)
+    check_num_nodes(g, xj)
+    use_w = bool(getattr(l, "use_edge_weight", False)) and g.w is not None
+    if edge_weight is None and not use_w and norm_fn is None:
+        plan = g.plan()
+        out = unrows(_GCNPropagateFn.apply(_f32(rows(xj), plan.device), plan, _gcn_c(g)))
+    else:
+        nf = norm_fn or default_norm_fn
+        if edge_weight is not None:
+            d = degree(g, torch.float32, dir="in", edge_weight=edge_weight)
+        else:
+            d = degree(g, torch.float32, dir="in", edge_weight=bool(getattr(l, "use_edge_weight", False)))
+        c = nf(d)
+        xs = xj * c.reshape(1, -1)
+        if edge_weight is not None:
+            out = propagate(e_mul_xj, g, operator.add, xj=xs, e=edge_weight)
+        elif use_w:
+            out = propagate(w_mul_xj, g, operator.add, xj=xs)
+        else:
+            out = propagate(copy_xj, g, operator.add, xj=xs)
+        out = out * c.reshape(1, -1)
+    if Dout >= Din:
+        out = _matmul(weight, out)
+    return _sigma(l)(_add_bias(out, _bias(l)))
+
+
+def glorot_uniform(*shape, device=None) -> torch.Tensor:
+    """Flux.glorot_uniform: U(-s, s), s = sqrt(24 / (fan_in + fan_out)) / 2... = sqrt(6/(fan_in+fan_out))."""
+    fan_out, fan_in = shape[0], shape[1] if len(shape) > 1 else shape[0]
+    s = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(*shape, device=device) * 2 - 1) * s
+
+
+class GCNConv(torch.nn.Module):
+    """GCNConv(in => out, σ=identity; bias=true, add_self_loops=true, use_edge_weight=false)
+    — GraphNeuralNetworks/src/layers/conv.jl:77-104."""
+
+    def __init__(self, ch_in: int, ch_out: int, sigma: Callable = identity, *, bias: bool = True,
+                 add_self_loops: bool = True, use_edge_weight: bool = False, device=None):
+        super().__init__()
+        self.weight = torch.nn.Parameter(glorot_uniform(ch_out, ch_in, device=device))
+        self.bias = torch.nn.Parameter(torch.zeros(ch_out, device=device)) if bias else None
+        self.sigma = sigma
+        self.add_self_loops = add_self_loops
+        self.use_edge_weight = use_edge_weight
+
+    def forward(self, g: GNNGraph, x: torch.Tensor, edge_weight=None, *, norm_fn=None, conv_weight=None):
+        return gcn_conv(self, g, x, edge_weight, norm_fn, conv_weight)
+
+
+# ------------------------------------------------------------------------------------------- GATConv
+class _GATAggregateFn(torch.autograd.Function):
+    """Fused logits -> leakyrelu -> neighbourhood softmax -> α-weighted sum: gnnb_gat_aggregate(+_bwd)."""
+
+    @staticmethod
+    def forward(ctx, Wx_rows, el_rows, er_rows, plan, slope):
+        N, H, Cc = Wx_rows.shape
+        out = torch.empty_like(Wx_rows)
+        smax = torch.empty((N, H), dtype=torch.float32, device=Wx_rows.device)
+        ssum = torch.empty((N, H), dtype=torch.float32, device=Wx_rows.device)
+        with torch.cuda.device(plan.device):
+            _lib.check(lib.gnnb_gat_aggregate(plan.h, Wx_rows.data_ptr(), el_rows.data_ptr(), er_rows.data_ptr(),
+                                              Cc, H, slope, out.data_ptr(), None, smax.data_ptr(),
+                                              ssum.data_ptr(), _stream(plan.device)))
+        ctx.plan, ctx.slope, ctx.dims = plan, slope, (Cc, H)
+        ctx.save_for_backward(Wx_rows, el_rows, er_rows, smax, ssum)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Wx_rows, el_rows, er_rows, smax, ssum = ctx.saved_tensors
+        Cc, H = ctx.dims
+        dout = dout.contiguous()
+        dWx = torch.empty_like(Wx_rows)
+        del_ = torch.empty_like(el_rows)
+        der = torch.empty_like(er_rows)
+        with torch.cuda.device(ctx.plan.device):
+            _lib.check(lib.gnnb_gat_aggregate_bwd(ctx.plan.h, Wx_rows.data_ptr(), el_rows.data_ptr(),
+                                                  er_rows.data_ptr(), smax.data_ptr(), ssum.data_ptr(),
+                                                  dout.data_ptr(), Cc, H, ctx.slope, dWx.data_ptr(),
+                                                  del_.data_ptr(), der.data_ptr(), _stream(ctx.plan.device)))
+        return dWx, del_, der, None, None
+
+
+def gat_message(l, Wxi, Wxj, e):
+    """GNNlib/src/layers/conv.jl:152-167 (generic path; arrays are (C, H, E))."""
+    _, chout = l.channel
+    heads = l.heads
+    if e is None:
+        Wxx = torch.cat([Wxi, Wxj], dim=0)
+    else:
+        We = l.dense_e(e)
+        We = _jl_reshape3(We, chout, heads)  # chout × nheads × nedges
+        Wxx = torch.cat([Wxi, Wxj, We], dim=0)
+    aWW = (l.a.unsqueeze(-1) * Wxx).sum(dim=0, keepdim=True)  # 1 × nheads × nedges
+    logα = torch.nn.functional.leaky_relu(aWW, float(l.negative_slope))
+    return {"logα": logα, "Wxj": Wxj}
+
+
+def _jl_reshape3(x: torch.Tensor, c: int, h: int) -> torch.Tensor:
+    """Julia reshape((c*h, N) -> (c, h, N)) on column-major data = view rows (N, c*h) as (N, h, c)."""
+    r = rows(x)
+    return unrows(r.reshape(r.shape[0], h, c))
+
+
+def gat_conv(l, g: GNNGraph, x: torch.Tensor, e: Optional[torch.Tensor] = None, *, fused: bool = True):
+    """GNNlib/src/layers/conv.jl:112-150.  Without edge features the edge part (two gathers, vcat, logits,
+    neighbourhood softmax, α .* Wxj, scatter) is ONE fused kernel; with edge features (or fused=False) the
+    reference's own composition runs on the generic gather/scatter kernels."""
+    check_num_nodes(g, x)
+    dense_e = getattr(l, "dense_e", None)
+    assert not (e is None and dense_e is not None), "Input edge features required for this layer"
+    assert not (e is not None and dense_e is None), "Input edge features were not specified in the layer constructor"
+    xj, xi = expand_srcdst(g, x)
+    if l.add_self_loops:
+        assert e is None, "Using edge features and setting add_self_loops=true at the same time is not yet supported."
+        g = add_self_loops(g)
+    _, chout = l.channel
+    heads = l.heads
+    Wxj = _jl_reshape3(l.dense_x(xj), chout, heads)  # chout × heads × N
+    Wxi = Wxj
+    if xi is not xj:
+        Wxi = _jl_reshape3(l.dense_x(xi), chout, heads)
+    if fused and e is None and xi is xj:
+        plan = g.plan()
+        Wr = _f32(rows(Wxj), plan.device)                       # (N, H, C)
+        a = l.a                                                 # (2C, H)
+        el = (Wr * a[:chout, :].t().unsqueeze(0)).sum(-1)       # (N, H): rows 1..C pair with the target
+        er = (Wr * a[chout:, :].t().unsqueeze(0)).sum(-1)       # rows C+1..2C pair with the source
+        out = unrows(_GATAggregateFn.apply(Wr, el.contiguous(), er.contiguous(), plan, float(l.negative_slope)))
+    else:
+        m = apply_edges(Fix1(gat_message, l), g, Wxi, Wxj, e)
+        α = softmax_edge_neighbors(g, m["logα"])
+        p = float(getattr(l, "dropout", 0.0) or 0.0)
+        if p > 0:
+            α = torch.nn.functional.dropout(α, p, training=getattr(l, "training", True))
+        β = α * m["Wxj"]
+        out = aggregate_neighbors(g, operator.add, β)
+    if not l.concat:
+        out = out.mean(dim=1, keepdim=True)
+    out = unrows(rows(out).reshape(out.shape[-1], -1))  # reshape(x, :, size(x, 3))
+    return _sigma(l)(_add_bias(out, _bias(l)))
+
+
+class _Dense(torch.nn.Module):
+    """Flux.Dense(in => out; bias) on Julia-shaped arrays."""
+
+    def __init__(self, ch_in, ch_out, bias=True, device=None):
+        super().__init__()
+        self.weight = torch.nn.Parameter(glorot_uniform(ch_out, ch_in, device=device))
+        self.bias = torch.nn.Parameter(torch.zeros(ch_out, device=device)) if bias else None
+
+    def forward(self, x):
+        return _add_bias(_matmul(self.weight, x), self.bias)
+
+
+class GATConv(torch.nn.Module):
+    """GATConv(in => out, σ=identity; heads=1, concat=true, negative_slope=0.2, add_self_loops=true, dropout=0)
+    — GraphNeuralNetworks/src/layers/conv.jl:309-346 (ein = 0: no edge features)."""
+
+    def __init__(self, ch_in: int, ch_out: int, sigma: Callable = identity, *, heads: int = 1,
+                 concat: bool = True, negative_slope: float = 0.2, bias: bool = True,
+                 add_self_loops: bool = True, dropout: float = 0.0, device=None):
+        super().__init__()
+        self.dense_x = _Dense(ch_in, ch_out * heads, bias=False, device=device)
+        self.dense_e = None
+        self.a = torch.nn.Parameter(glorot_uniform(2 * ch_out, heads, device=device))
+        nb = ch_out * heads if concat else ch_out
+        self.bias = torch.nn.Parameter(torch.zeros(nb, device=device)) if bias else None
+        self.sigma = sigma
+        self.negative_slope = negative_slope
+        self.channel = (ch_in, ch_out)
+        self.heads = heads
+        self.concat = concat
+        self.add_self_loops = add_self_loops
+        self.dropout = dropout
+
+    def forward(self, g: GNNGraph, x: torch.Tensor, e=None, **kw):
+        return gat_conv(self, g, x, e, **kw)
+
+
+# ------------------------------------------------------------------------------------------ SAGEConv
+def sage_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:277-283: σ.(W * vcat(xi, propagate(copy_xj, g, aggr, xj)) .+ b).
+    W is (out, 2·in): its first `in` columns multiply x_i, the rest the aggregated neighbours, so the vcat
+    temporary is never built."""
+    check_num_nodes(g, x)
+    xj, xi = expand_srcdst(g, x)
+    m = propagate(copy_xj, g, l.aggr, xj=xj)
+    W = l.weight
+    din = xi.shape[0]
+    out = unrows(torch.addmm(rows(xi) @ W[:, :din].t(), rows(m), W[:, din:].t()))
+    return _sigma(l)(_add_bias(out, _bias(l)))
+
+
+class SAGEConv(torch.nn.Module):
+    """SAGEConv(in => out, σ=identity; aggr=mean, bias=true) — GraphNeuralNetworks/src/layers/conv.jl:770-787."""
+
+    def __init__(self, ch_in: int, ch_out: int, sigma: Callable = identity, *, aggr=mean, bias: bool = True,
+                 device=None):
+        super().__init__()
+        self.weight = torch.nn.Parameter(glorot_uniform(ch_out, 2 * ch_in, device=device))
+        self.bias = torch.nn.Parameter(torch.zeros(ch_out, device=device)) if bias else None
+        self.sigma = sigma
+        self.aggr = aggr
+
+    def forward(self, g: GNNGraph, x: torch.Tensor):
+        return sage_conv(self, g, x)

@@ -1,0 +1,211 @@
+/*
+ * gnnb200.h — C ABI of libgnnb200.so, the B200-native (sm_100a) message-passing engine that sits
+ * behind GNNlib.jl's `propagate` / `apply_edges` / `aggregate_neighbors` hot path.
+ *
+ * Every entry point below replaces one reference interface; the citation after "replaces:" is
+ * file:line under the reference tree (CarloLucibello/GraphNeuralNetworks.jl @ e46d1b04).  The Julia
+ * binding a maintainer would add (`ccall`s from a package extension that mirrors
+ * GNNlib/ext/GNNlibCUDAExt.jl:13-32) is shown in INTEGRATION.md and julia/GNNlibB200Ext.jl.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / CUDA types (`stream` is a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).
+ *   - every function returns a gnnb_status; 0 = ok.  gnnb_last_error() gives the thread-local text.
+ *     The host shim maps GNNB_ESIZE -> AssertionError (GNNGraphs/src/utils.jl:1-28) and
+ *     GNNB_EINVAL -> ArgumentError (GNNlib/src/layers/conv.jl:3-10,22).
+ *   - feature arrays are Julia column-major (D, N): node n owns D contiguous floats at x + n*D.
+ *     Edge arrays (K, E) likewise, in the COO order of the graph the handle was created from.
+ *   - "device" entry points take device pointers, are asynchronous on `stream`, never allocate
+ *     caller-visible memory and never free caller memory.  The only library-owned object is the
+ *     opaque graph plan.  "_host" entry points take HOST pointers and do the H2D/D2H themselves.
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns GNNB_ECUDA.
+ */
+#ifndef GNNB200_H
+#define GNNB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GNNB_OK = 0,
+    GNNB_EINVAL = 1,       /* bad argument value        -> ArgumentError  */
+    GNNB_ESIZE = 2,        /* size mismatch             -> AssertionError */
+    GNNB_ECUDA = 3,        /* CUDA runtime error / no device              */
+    GNNB_ENOMEM = 4,       /* device allocation failed                    */
+    GNNB_EUNSUPPORTED = 5, /* valid in the reference, not in this build   */
+    GNNB_EINDEX = 6        /* node index out of [base, base+N) -> AssertionError (convert.jl:49-54) */
+} gnnb_status;
+
+/* message functions with a fused path (GNNlib/src/msgpass.jl:162-208) */
+typedef enum {
+    GNNB_COPY_XJ = 0,  /* copy_xj(xi,xj,e) = xj                 msgpass.jl:165 */
+    GNNB_W_MUL_XJ = 1  /* w_mul_xj / e_mul_xj with a vector e   msgpass.jl:191-208 */
+} gnnb_msg;
+
+/* aggregations NNlib.scatter supports that the layers use */
+typedef enum { GNNB_SUM = 0, GNNB_MEAN = 1, GNNB_MAX = 2, GNNB_MIN = 3 } gnnb_aggr;
+
+/* which end of an edge */
+typedef enum { GNNB_SRC = 0, GNNB_DST = 1 } gnnb_end;
+
+/* degree direction (GNNGraphs/src/query.jl:314-369 `dir`) */
+typedef enum { GNNB_DIR_OUT = 0, GNNB_DIR_IN = 1, GNNB_DIR_BOTH = 2 } gnnb_dir;
+
+typedef struct gnnb_graph* gnnb_graph_t;
+
+/* ---------------------------------------------------------------- library */
+
+/* thread-local text of the last failure on this thread ("" if none) */
+const char* gnnb_last_error(void);
+/* library version string, e.g. "gnnb200 0.1 sm_100a" */
+const char* gnnb_version(void);
+/* number of CUDA devices visible (0 when there is none; never fails) */
+int gnnb_device_count(void);
+/* kernels launched by this library on the calling process since load (bench.py `gpu_launches`) */
+int64_t gnnb_launch_count(void);
+
+/* ------------------------------------------------------------------ graph
+ * replaces: the COO GNNGraph value `(s, t)` that `edge_index(g)` hands to the hot path
+ *           (GNNGraphs/src/query.jl:12-14, GNNGraphs/src/gnngraph.jl:108-117) plus the range
+ *           validation of `to_coo` (GNNGraphs/src/convert.jl:49-54).
+ * Builds the device plan: int32 0-based COO copy, CSR-by-target (stable in COO order: rowptr, col,
+ * sorted targets, edge-id permutation) and, lazily on first backward/transposed use, CSR-by-source.
+ *   src,dst      : E indices, `index_bytes` = 4 (Int32) or 8 (Int64), `index_base` = 1 (Julia) or 0
+ *   num_src/dst  : node counts of the two ends (equal for a GNNGraph; they differ for the
+ *                  [local|halo] source space of a node-partitioned shard)
+ *   on_device    : 0 = src/dst are host pointers, 1 = device pointers
+ * Errors: GNNB_EINDEX if any index is outside [base, base+num); GNNB_ESIZE if E or N is negative or
+ *         E >= 2^31 (per-GPU shards are int32-indexed), GNNB_EINVAL for bad index_bytes/base. */
+int gnnb_graph_create(gnnb_graph_t* out, const void* src, const void* dst, int64_t num_edges,
+                      int64_t num_src, int64_t num_dst, int index_bytes, int index_base,
+                      int on_device, void* stream);
+int gnnb_graph_destroy(gnnb_graph_t g);
+
+/* replaces: add_self_loops(g::GNNGraph{<:COO_T}) (GNNGraphs/src/transform.jl:12-28): a NEW plan
+ * whose COO is [s; 1:n], [t; 1:n] (loops appended after the originals, existing loops kept).
+ * Requires num_src == num_dst (GNNB_ESIZE otherwise). */
+int gnnb_graph_add_self_loops(gnnb_graph_t g, gnnb_graph_t* out, void* stream);
+
+/* num_edges, num_src, num_dst of a plan */
+int gnnb_graph_info(gnnb_graph_t g, int64_t* num_edges, int64_t* num_src, int64_t* num_dst);
+
+/* Copy the plan's index arrays to HOST buffers (NULL = skip) for bit-exact checks:
+ *   transposed=0: CSR by target  (rowptr[num_dst+1], col = source of each sorted edge)
+ *   transposed=1: CSR by source  (rowptr[num_src+1], col = target of each sorted edge)
+ *   eid[k] = 0-based COO position of sorted edge k (stable: ascending within a row).
+ * replaces nothing in the reference (it has no CSR type); rowptr differences must
+ * equal degree(g; dir=:in / :out) exactly (GNNGraphs/test/query.jl:49-58). */
+int gnnb_graph_csr(gnnb_graph_t g, int transposed, int32_t* rowptr, int32_t* col, int32_t* eid,
+                   void* stream);
+
+/* replaces: degree(g, Float32; dir, edge_weight) -> _degree (GNNGraphs/src/query.jl:314-331,355-369)
+ * w = NULL -> counts (exact integers stored as float), else sum of w (COO order, length E).
+ * out has num_dst (IN), num_src (OUT) entries; BOTH requires num_src == num_dst. */
+int gnnb_degree(gnnb_graph_t g, int dir, const float* w, float* out, void* stream);
+
+/* ------------------------------------------------------- gather / scatter
+ * replaces: GNNGraphs._gather -> NNlib.gather (GNNGraphs/src/gatherscatter.jl:1-5):
+ *           out[:,k] = x[:, idx[k]], idx = s (GNNB_SRC) or t (GNNB_DST), COO order. (D,N)->(D,E) */
+int gnnb_gather(gnnb_graph_t g, int which, const float* x, int64_t D, float* out, void* stream);
+
+/* replaces: GNNGraphs._scatter -> NNlib.scatter(aggr, m, t; dstsize=(D,n))
+ *           (GNNGraphs/src/gatherscatter.jl:12-18; called from aggregate_neighbors, msgpass.jl:145-149)
+ * m is (D,E) in COO order, out (D, num_dst).  Empty targets get the op's neutral element:
+ * 0 for SUM/MEAN, -Inf for MAX, +Inf for MIN (NNlib semantics).
+ * which = GNNB_DST scatters by target (aggregate_neighbors); GNNB_SRC scatters by source into
+ * (D, num_src) (the pullback of gather by s). */
+int gnnb_scatter(gnnb_graph_t g, int which, int aggr, const float* m, int64_t D, float* out,
+                 void* stream);
+
+/* ------------------------------------------------------------- propagate
+ * replaces: propagate(copy_xj | w_mul_xj | e_mul_xj(vector e), g, + | mean | max | min; xj)
+ *           = aggregate_neighbors(g, aggr, apply_edges(f, g, xi, xj, e))   (msgpass.jl:71-79),
+ *           its CPU SpMM specialisations (msgpass.jl:215-238) and the CUDA-ext re-routing
+ *           (GNNlib/ext/GNNlibCUDAExt.jl:13-32) — fused: no (D,E) intermediate.
+ *   out[:,i] = ct[i] * AGG_{k in N(i)} ( w[k] * cs[s_k] * x[:, s_k] )
+ *   x  (D, num_src), out (D, num_dst); w NULL or E floats in COO order (required for W_MUL_XJ);
+ *   cs NULL or num_src floats, ct NULL or num_dst floats: optional per-node scales fused into the
+ *   load / store (GCN's 1/sqrt(d), conv.jl:57-67).  MEAN divides by the in-degree (0 for isolated).
+ *   transposed != 0 runs the same reduction on the reversed graph (x is (D,num_dst), out (D,num_src)):
+ *   that is the pullback of the SUM/MEAN forward w.r.t. xj. */
+int gnnb_propagate(gnnb_graph_t g, int transposed, int msg, int aggr, const float* x,
+                   const float* w, const float* cs, const float* ct, int64_t D, float* out,
+                   void* stream);
+
+/* Pullbacks of gnnb_propagate (what Zygote computes today through NNlib's rrules).
+ *   dout (D,num_dst).  dx (D,num_src) or NULL.  dw (E, COO order) or NULL (W_MUL_XJ only).
+ *   SUM/MEAN: dx[:,j] = cs[j] * sum_{k: s_k=j} w_k * ct'[t_k] * dout[:,t_k]   (ct' = ct/deg for MEAN)
+ *             dw[k]   = ct'[t_k] * cs[s_k] * <dout[:,t_k], x[:,s_k]>
+ *   MAX/MIN : needs x and the forward output `out_fwd`; every tied arg-extremum receives the
+ *             gradient (NNlib rule): dx[:,j] += w_k cs[j] ct[t_k] dout[:,t_k] .* (m_k .== out_fwd[:,t_k]/ct[t_k])
+ *             (dw unsupported for MAX/MIN: GNNB_EUNSUPPORTED). */
+int gnnb_propagate_bwd(gnnb_graph_t g, int msg, int aggr, const float* dout, const float* x,
+                       const float* w, const float* cs, const float* ct, const float* out_fwd,
+                       int64_t D, float* dx, float* dw, void* stream);
+
+/* ------------------------------------------------------------ edge softmax
+ * replaces: softmax_edge_neighbors(g, e) (GNNlib/src/utils.jl:84-97): for every leading index,
+ *           a softmax over the edges that share a target.  e, out are (K,E) in COO order. */
+int gnnb_softmax_edge_neighbors(gnnb_graph_t g, const float* e, int64_t K, float* out, void* stream);
+/* pullback: de_k = a_k (da_k - sum_{k' in N(i)} a_k' da_k'), a = forward output. */
+int gnnb_softmax_edge_neighbors_bwd(gnnb_graph_t g, const float* alpha, const float* dalpha,
+                                    int64_t K, float* de, void* stream);
+
+/* --------------------------------------------------------------- GCN core
+ * replaces: the message-passing core of gcn_conv (GNNlib/src/layers/conv.jl:52-67):
+ *     d = degree(g, T; dir=:in, edge_weight); c = 1 ./ sqrt.(d)       (default norm_fn, conv.jl:99)
+ *     out = (propagate(copy_xj | e_mul_xj, g, +, xj = x .* c')) .* c'
+ * `g` must already carry the self loops if the layer adds them (gnnb_graph_add_self_loops).
+ * w NULL or E floats (COO order of g, loop weights included).  c_out (num_dst floats) receives c
+ * (kept by the caller for the backward).  transposed=1 computes the pullback w.r.t. x given dout
+ * and the forward's c:  dx = c .* (A^T-propagate(dout .* c)). */
+int gnnb_gcn_norm(gnnb_graph_t g, const float* w, float* c_out, void* stream);
+int gnnb_gcn_propagate(gnnb_graph_t g, int transposed, const float* x, const float* w,
+                       const float* c, int64_t D, float* out, void* stream);
+
+/* --------------------------------------------------------------- GAT core
+ * replaces: the edge part of gat_conv + gat_message (GNNlib/src/layers/conv.jl:136-141,152-167):
+ *     logα_k[h] = leakyrelu(el[h,t_k] + er[h,s_k], slope)          (a·[Wx_i;Wx_j])
+ *     α = softmax_edge_neighbors(g, logα);  out[:,h,i] = Σ_k α_k[h] Wx[:,h,s_k]
+ * Wx (C,H,num_src), el (H,num_dst), er (H,num_src), out (C,H,num_dst).
+ * Optional outputs (NULL = skip): alpha (H,E) in COO order; seg_max, seg_sum (H,num_dst) — the
+ * per-target softmax statistics the backward recomputes α from. */
+int gnnb_gat_aggregate(gnnb_graph_t g, const float* Wx, const float* el, const float* er,
+                       int64_t C, int64_t H, float slope, float* out, float* alpha,
+                       float* seg_max, float* seg_sum, void* stream);
+/* pullback: given dout (C,H,num_dst) and the forward statistics, produce
+ *   dWx (C,H,num_src) = Σ_{k: s_k=j} α_k dout[:,:,t_k]        (attention-weighted transposed pull)
+ *   del (H,num_dst), der (H,num_src): gradients of the two per-node logit terms. */
+int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, const float* er,
+                           const float* seg_max, const float* seg_sum, const float* dout,
+                           int64_t C, int64_t H, float slope, float* dWx, float* del, float* der,
+                           void* stream);
+
+/* ------------------------------------------------------ host-buffer entries
+ * The reference-facing call with HOST arrays (what a CPU-array caller of `propagate` has): copies
+ * x (and w) to the device, runs the fused pass, copies `out` back; synchronous.  Used for the
+ * end-to-end number (bench.py `e2e`).  Same semantics as gnnb_propagate / gnnb_gcn_propagate. */
+int gnnb_propagate_host(gnnb_graph_t g, int transposed, int msg, int aggr, const float* x_host,
+                        const float* w_host, int64_t D, float* out_host);
+int gnnb_gcn_propagate_host(gnnb_graph_t g, int transposed, const float* x_host,
+                            const float* w_host, int64_t D, float* out_host);
+
+/* ------------------------------------------------------------- generators
+ * RMAT edge list (ours; the reference has none): Graph500 a,b,c,d = .57,.19,.19,.05,
+ * counter-based splitmix64 keyed on (seed, edge id, retry); edges with an endpoint >= N are redrawn;
+ * duplicates and self loops kept; generation order.  Writes int64 1-based src/dst DEVICE arrays.
+ * The oracle has the bit-identical CPU generator (oracle/gnn_oracle.c: orc_rmat). */
+int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t* src_dev,
+                    int64_t* dst_dev, void* stream);
+
+/* tuning knob for experiments: edges per work chunk of the segmented-reduce kernels (default 128;
+ * power of two in [32, 4096]); affects plans created afterwards. */
+int gnnb_set_chunk_edges(int chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNB200_H */

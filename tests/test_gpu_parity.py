@@ -1,0 +1,463 @@
+"""Parity of the CUDA path (through the Python mirror -> C ABI -> sm_100a kernels) with the CPU oracle.
+
+Bar (BASELINE.json north_star): bit-exact for index arithmetic; fp32 aggregations within 1e-5 relative
+(normwise, the reference's `isapprox` semantics, GNNlib/test/test_module.jl:75-151) of the fp64 oracle — the
+tests below use the tighter 2e-6 — and bit-exact against the fp32 oracle wherever a row is reduced by a single
+group in COO order (rows <= chunk edges, sum/max/min).
+"""
+import ctypes as C
+import operator
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-6
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    fin = np.isfinite(b)
+    assert (np.isfinite(a) == fin).all() and (a[~fin] == b[~fin]).all()
+    return np.linalg.norm(a[fin] - b[fin]) / max(np.linalg.norm(b[fin]), 1e-30)
+
+
+def make_graph(rng, n, E, hubs=0, hub_deg=0, empty_frac=0.3):
+    """random multigraph; the top `empty_frac` of the node ids receive no edges; `hubs` targets get hub_deg extra"""
+    hi = max(1, int(n * (1 - empty_frac)))
+    s = rng.integers(1, n + 1, E)
+    t = rng.integers(1, hi + 1, E)
+    for h in range(hubs):
+        s = np.concatenate([s, rng.integers(1, n + 1, hub_deg)])
+        t = np.concatenate([t, np.full(hub_deg, 1 + 3 * h)])
+    p = rng.permutation(len(s))
+    return s[p].astype(np.int64), t[p].astype(np.int64)
+
+
+def jl(x_rows, dev="cuda"):
+    """numpy rows (N, ...) -> Julia-shaped column-major device tensor (..., N)"""
+    import gnnb200
+    return gnnb200.unrows(torch.as_tensor(np.ascontiguousarray(x_rows), dtype=torch.float32).to(dev))
+
+
+def np_rows(x_jl):
+    import gnnb200
+    return gnnb200.rows(x_jl.detach()).cpu().numpy()
+
+
+GRAPHS = {
+    "small": dict(n=37, E=150),
+    "empty_rows": dict(n=200, E=300, empty_frac=0.6),
+    "hubs": dict(n=500, E=3000, hubs=3, hub_deg=1000),     # rows far longer than the 128-edge chunk
+    "sparse": dict(n=5000, E=40),                          # rows >> edges: row-parallel empty fill path
+}
+
+
+@pytest.fixture(scope="module", params=list(GRAPHS))
+def graph(request, gnn):
+    rng = np.random.default_rng(list(GRAPHS).index(request.param))
+    kw = GRAPHS[request.param]
+    s, t = make_graph(rng, **kw)
+    g = gnn.GNNGraph(s, t, num_nodes=kw["n"]).to("cuda")
+    return request.param, s, t, kw["n"], g
+
+
+# ------------------------------------------------------------------------------------------ index work
+def test_csr_bit_exact(graph, oracle, gnn):
+    _, s, t, n, g = graph
+    p = g.plan()
+    E = len(s)
+    for transposed, key, other in ((0, t, s), (1, s, t)):
+        rowptr = np.empty(n + 1, np.int32)
+        col = np.empty(E, np.int32)
+        eid = np.empty(E, np.int32)
+        gnn._lib.check(gnn._lib.lib.gnnb_graph_csr(p.h, transposed, rowptr.ctypes.data, col.ctypes.data,
+                                                   eid.ctypes.data, None))
+        r0, c0, p0 = oracle.csr(key, other, n)
+        assert (rowptr == r0).all() and (col == c0).all() and (eid == p0).all()
+    # rowptr differences == degree(g; dir=:in) exactly
+    assert (gnn.degree(g, dir="in").cpu().numpy() == oracle.degree(s, t, n, "in").astype(np.int64)).all()
+    assert (gnn.degree(g, dir="out").cpu().numpy() == oracle.degree(s, t, n, "out").astype(np.int64)).all()
+    assert (gnn.degree(g, dir="both").cpu().numpy() == oracle.degree(s, t, n, "both").astype(np.int64)).all()
+
+
+def test_self_loop_plan_bit_exact(graph, oracle, gnn):
+    _, s, t, n, g = graph
+    g.plan()
+    gnn._lib.check(gnn._lib.lib.gnnb_graph_csr(g.plan().h, 1, None, None, None, None))   # build by_src too
+    g2 = gnn.add_self_loops(g)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    assert (g2.s.cpu().numpy() == s2).all() and (g2.t.cpu().numpy() == t2).all()
+    E2 = len(s2)
+    for transposed, key, other in ((0, t2, s2), (1, s2, t2)):
+        rowptr = np.empty(n + 1, np.int32); col = np.empty(E2, np.int32); eid = np.empty(E2, np.int32)
+        gnn._lib.check(gnn._lib.lib.gnnb_graph_csr(g2.plan().h, transposed, rowptr.ctypes.data, col.ctypes.data,
+                                                   eid.ctypes.data, None))
+        r0, c0, p0 = oracle.csr(key, other, n)
+        assert (rowptr == r0).all() and (col == c0).all() and (eid == p0).all()
+
+
+def test_index_inputs_and_validation(gnn, oracle):
+    s = np.array([1, 1, 2, 3]); t = np.array([2, 2, 2, 4])
+    ref = oracle.csr(t, s, 4)
+    for dt in (torch.int64, torch.int32):
+        for dev in ("cpu", "cuda"):
+            g = gnn.GNNGraph(torch.as_tensor(s, dtype=dt, device=dev), torch.as_tensor(t, dtype=dt, device=dev))
+            rowptr = np.empty(5, np.int32); col = np.empty(4, np.int32); eid = np.empty(4, np.int32)
+            gnn._lib.check(gnn._lib.lib.gnnb_graph_csr(g.plan().h, 0, rowptr.ctypes.data, col.ctypes.data,
+                                                       eid.ctypes.data, None))
+            assert (rowptr == ref[0]).all() and (col == ref[1]).all() and (eid == ref[2]).all()
+    # 1 <= idx <= num_nodes (GNNGraphs/src/convert.jl:49-54) -> AssertionError
+    for bad_s, bad_t in (([0, 1], [1, 2]), ([1, 2], [1, 5])):
+        with pytest.raises(AssertionError):
+            gnn.GNNGraph(bad_s, bad_t, num_nodes=4).plan()
+
+
+def test_degree_golden(gnn):
+    # GNNGraphs/test/query.jl:49-58,71-87 on the GPU
+    s, t = [1, 1, 2, 3], [2, 2, 2, 4]
+    g = gnn.GNNGraph(s, t).cuda()
+    assert gnn.degree(g).tolist() == [2, 1, 1, 0] == gnn.degree(g, dir="out").tolist()
+    assert gnn.degree(g, dir="in").tolist() == [0, 3, 0, 1]
+    assert gnn.degree(g, dir="both").tolist() == [2, 4, 1, 1]
+    assert gnn.degree(g, torch.float32).dtype == torch.float32
+    w = torch.tensor([0.1, 2.1, 1.2, 1.0])
+    gw = gnn.GNNGraph((s, t, w)).cuda()
+    np.testing.assert_allclose(gnn.degree(gw).cpu(), [2.2, 1.2, 1.0, 0.0], rtol=1e-6)
+    assert gnn.degree(gw, edge_weight=False).tolist() == [2, 1, 1, 0]
+    np.testing.assert_allclose(gnn.degree(gw, edge_weight=2 * w.cuda()).cpu(), [4.4, 2.4, 2.0, 0.0], rtol=1e-6)
+
+
+def test_rmat_gpu_equals_cpu(gnn, oracle):
+    for n, E in ((1000, 5000), (100000, 300000)):
+        g = gnn.rmat_graph(n, E, 17)
+        s, t = oracle.rmat(n, E, 17)
+        assert (g.s.cpu().numpy() == s).all() and (g.t.cpu().numpy() == t).all()
+
+
+# ---------------------------------------------------------------------------------------- fused propagate
+@pytest.mark.parametrize("D", [1, 3, 7, 10, 16, 20, 64, 128, 132, 256, 512, 300, 1433])
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+def test_propagate_copy_xj(graph, oracle, gnn, D, aggr):
+    name, s, t, n, g = graph
+    if D > 300 and name != "small":
+        pytest.skip("wide rows only on the small graph")
+    rng = np.random.default_rng(D)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    got = np_rows(gnn.propagate(gnn.copy_xj, g, aggr, xj=jl(x)))
+    ref64 = oracle.propagate_unfused(aggr, s, t, n, x.astype(np.float64))
+    assert rel(got, ref64) < TOL
+    if aggr in ("max", "min"):       # order independent: bit-exact
+        assert (got == oracle.propagate_unfused(aggr, s, t, n, x)).all()
+    elif name in ("small", "empty_rows", "sparse"):   # rows <= chunk: same summation order as NNlib's CPU scatter
+        assert (got == oracle.propagate_unfused(aggr, s, t, n, x)).all()
+
+
+@pytest.mark.parametrize("D", [1, 5, 16, 128, 260])
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+@pytest.mark.parametrize("fn", ["w_mul_xj", "e_mul_xj"])
+def test_propagate_weighted(graph, oracle, gnn, D, aggr, fn):
+    name, s, t, n, g = graph
+    rng = np.random.default_rng(D + 1)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    w = rng.random(len(s)).astype(np.float32) - 0.3
+    wt = torch.as_tensor(w).cuda()
+    if fn == "w_mul_xj":
+        got = gnn.propagate(gnn.w_mul_xj, gnn.set_edge_weight(g, wt), aggr, xj=jl(x))
+    else:
+        got = gnn.propagate(gnn.e_mul_xj, g, aggr, xj=jl(x), e=wt)
+    got = np_rows(got)
+    ref64 = oracle.propagate_unfused(aggr, s, t, n, x.astype(np.float64), w.astype(np.float64))
+    assert rel(got, ref64) < TOL
+    if aggr != "mean" and name != "hubs":
+        assert (got == oracle.propagate_unfused(aggr, s, t, n, x, w)).all()
+
+
+def test_propagate_matches_dense_adjacency(gnn, oracle):
+    # GNNlib/test/msgpass.jl:69-116 on the GPU: ≈ X * Adj and ≈ X * A
+    n = 128
+    rng = np.random.default_rng(0)
+    A = (rng.random((n, n)) < 0.1) * rng.random((n, n))
+    g = gnn.GNNGraph(A.astype(np.float32)).cuda()
+    X = rng.random((10, n)).astype(np.float32)
+    Xd = gnn.colmajor(torch.as_tensor(X).cuda())
+    Adj = (A > 0).astype(np.float64)
+    y = gnn.propagate(gnn.copy_xj, g, operator.add, xj=Xd).cpu().numpy()
+    assert rel(y, X.astype(np.float64) @ Adj) < TOL
+    y = gnn.propagate(lambda xi, xj, e: xj, g, operator.add, xj=Xd).cpu().numpy()       # unfused path
+    assert rel(y, X.astype(np.float64) @ Adj) < TOL
+    ref = X.astype(np.float64) @ A.astype(np.float32).astype(np.float64)
+    y = gnn.propagate(gnn.w_mul_xj, g, operator.add, xj=Xd).cpu().numpy()
+    assert rel(y, ref) < TOL
+    y = gnn.propagate(gnn.e_mul_xj, g, operator.add, xj=Xd, e=g.w).cpu().numpy()
+    assert rel(y, ref) < TOL
+    y = gnn.propagate(lambda xi, xj, e: e.reshape(1, -1) * xj, g, operator.add, xj=Xd, e=g.w).cpu().numpy()
+    assert rel(y, ref) < TOL
+
+
+def test_propagate_shapes_isolated_nodes_and_empty_graph(gnn):
+    # GNNlib/test/msgpass.jl:10-26
+    g1 = gnn.GNNGraph(list(range(1, 6)), list(range(1, 6)), num_nodes=6).cuda()
+    x1 = gnn.colmajor(torch.rand(1, 6).cuda())
+    y1 = gnn.propagate(lambda xi, xj, e: xj, g1, operator.add, xj=x1)
+    assert y1.shape == (1, 6) and y1[0, 5] == 0
+    y1 = gnn.propagate(gnn.copy_xj, g1, operator.add, xj=x1)
+    assert y1.shape == (1, 6) and y1[0, 5] == 0 and torch.equal(y1[:, :5], x1[:, :5])
+    g0 = gnn.GNNGraph(torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.int64), num_nodes=5).cuda()
+    x0 = gnn.colmajor(torch.rand(4, 5).cuda())
+    assert (gnn.propagate(gnn.copy_xj, g0, operator.add, xj=x0) == 0).all()
+    assert (gnn.propagate(gnn.copy_xj, g0, max, xj=x0) == -float("inf")).all()
+    assert (gnn.propagate(gnn.copy_xj, g0, min, xj=x0) == float("inf")).all()
+    # 3-D features (C, H, N): last dimension is the node dimension
+    x3 = gnn.jl_randn(3, 2, 6, device="cuda")
+    y3 = gnn.propagate(gnn.copy_xj, g1, gnn.mean, xj=x3)
+    assert y3.shape == (3, 2, 6) and torch.equal(y3[..., :5], x3[..., :5])
+
+
+def test_generic_message_functions(graph, oracle, gnn):
+    # apply_edges with NamedTuple-like containers, xi/xj/e all used (GNNlib/test/msgpass.jl:28-53)
+    _, s, t, n, g = graph
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((n, 6)).astype(np.float32)
+    e = rng.standard_normal((len(s), 6)).astype(np.float32)
+    m = gnn.apply_edges(lambda xi, xj, e: {"a": xi["u"] - xj["u"], "b": gnn.xi_dot_xj(xi["u"], xj["u"], None) + e[:1]},
+                        g, xi={"u": jl(x)}, xj={"u": jl(x), "v": jl(2 * x)}, e=jl(e))
+    a_ref = x[t - 1] - x[s - 1]
+    b_ref = (x[t - 1] * x[s - 1]).sum(1, keepdims=True) + e[:, :1]
+    assert rel(np_rows(m["a"]), a_ref) < TOL and rel(np_rows(m["b"]), b_ref) < TOL
+    out = gnn.aggregate_neighbors(g, gnn.mean, m)
+    assert rel(np_rows(out["a"]), oracle.scatter("mean", a_ref.astype(np.float64), t, n)) < TOL
+    assert rel(np_rows(out["b"]), oracle.scatter("mean", b_ref.astype(np.float64), t, n)) < TOL
+    assert gnn.aggregate_neighbors(g, operator.add, None) is None
+    # gather / scatter primitives, bit-exact data movement
+    xe = gnn.apply_edges(gnn.copy_xi, g, xi=jl(x))
+    assert (np_rows(xe) == x[t - 1]).all()
+    for aggr in ("+", "max", "min"):
+        got = np_rows(gnn.aggregate_neighbors(g, aggr, jl(e)))
+        assert rel(got, oracle.scatter(aggr, e.astype(np.float64), t, n)) < TOL
+
+
+# ------------------------------------------------------------------------------------------- pullbacks
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+@pytest.mark.parametrize("D", [3, 16, 128])
+def test_propagate_gradients(graph, oracle, gnn, aggr, D):
+    """Zygote/NNlib pullbacks restated through the oracle's gather/scatter."""
+    name, s, t, n, g = graph
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    if aggr in ("max", "min"):   # create exact ties
+        x = np.round(x * 2) / 2
+    dout = rng.standard_normal((n, D)).astype(np.float32)
+    w = (rng.random(len(s)) + 0.5).astype(np.float32)
+    for weighted in (False, True):
+        xt = jl(x).requires_grad_(True)
+        wt = torch.as_tensor(w).cuda().requires_grad_(True)
+        if weighted:
+            y = gnn.propagate(gnn.e_mul_xj, g, aggr, xj=xt, e=wt)
+        else:
+            y = gnn.propagate(gnn.copy_xj, g, aggr, xj=xt)
+        if aggr in ("max", "min"):
+            dd = np.where(np.isfinite(np_rows(y)), dout, 0).astype(np.float32)   # no gradient through ∓Inf rows
+        else:
+            dd = dout
+        if weighted and aggr in ("max", "min"):
+            wt2 = wt.detach()   # dw for max/min runs through the generic path only
+            y = gnn.propagate(gnn.e_mul_xj, g, aggr, xj=xt, e=wt2)
+        y.backward(jl(dd))
+        # oracle: m = w .* gather(x, s); out = scatter(aggr, m, t)
+        x64, w64, d64 = x.astype(np.float64), w.astype(np.float64), dd.astype(np.float64)
+        m = oracle.gather(x64, s) * (w64[:, None] if weighted else 1.0)
+        dg = oracle.gather(d64, t)
+        if aggr == "mean":
+            cnt = np.maximum(oracle.degree(s, t, n, "in", None, np.float64), 1)
+            dm = dg / cnt[t - 1][:, None]
+        elif aggr in ("max", "min"):
+            out = oracle.scatter(aggr, m, t, n)
+            dm = dg * (m == oracle.gather(out, t))
+        else:
+            dm = dg
+        dx_ref = oracle.scatter("+", dm * (w64[:, None] if weighted else 1.0), s, n)
+        assert rel(np_rows(xt.grad), dx_ref) < 5e-6
+        if weighted and aggr in ("+", "mean"):
+            dw_ref = (dm * oracle.gather(x64, s)).sum(1)
+            assert rel(wt.grad.cpu().numpy(), dw_ref) < 5e-6
+
+
+def test_generic_path_gradients(graph, oracle, gnn):
+    """gather/scatter autograd (the path an arbitrary message function takes) ≈ fused path gradients."""
+    _, s, t, n, g = graph
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((n, 8)).astype(np.float32)
+    dout = jl(rng.standard_normal((n, 8)).astype(np.float32))
+    for aggr in ("+", "mean", "max"):
+        a = jl(x).requires_grad_(True)
+        b = jl(x).requires_grad_(True)
+        ya = gnn.propagate(gnn.copy_xj, g, aggr, xj=a)
+        yb = gnn.propagate(lambda xi, xj, e: xj, g, aggr, xj=b)
+        fin = torch.isfinite(ya)
+        assert torch.equal(fin, torch.isfinite(yb))
+        d = torch.where(fin, dout, torch.zeros_like(dout))
+        ya.backward(d); yb.backward(d)
+        assert rel(ya.detach().cpu(), yb.detach().cpu()) < TOL
+        assert rel(a.grad.cpu(), b.grad.cpu()) < 5e-6
+
+
+# ---------------------------------------------------------------------------------------- edge softmax
+def test_softmax_edge_neighbors_golden(gnn):
+    # GNNlib/test/utils.jl:58-67
+    g2 = gnn.GNNGraph([1, 2, 3, 4], [5, 5, 6, 6]).cuda()
+    e2 = gnn.jl_randn(3, g2.num_edges, device="cuda")
+    z = gnn.softmax_edge_neighbors(g2, e2)
+    assert z.shape == e2.shape
+    assert torch.allclose(z[:, 0:2], torch.softmax(e2[:, 0:2], dim=1), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(z[:, 2:4], torch.softmax(e2[:, 2:4], dim=1), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("K", [1, 3, 8])
+def test_softmax_edge_neighbors_parity_and_grad(graph, oracle, gnn, K):
+    _, s, t, n, g = graph
+    rng = np.random.default_rng(K)
+    e = (3 * rng.standard_normal((len(s), K))).astype(np.float32)
+    et = jl(e).requires_grad_(True)
+    z = gnn.softmax_edge_neighbors(g, et)
+    ref = oracle.softmax_edge_neighbors(t, n, e.astype(np.float64))
+    assert rel(np_rows(z), ref) < TOL
+    da = rng.standard_normal((len(s), K))
+    z.backward(jl(da.astype(np.float32)))
+    # de_k = a_k (da_k - sum_{k' in N(i)} a_k' da_k')
+    T = oracle.scatter("+", ref * da, t, n)
+    de_ref = ref * (da - oracle.gather(T, t))
+    assert rel(np_rows(et.grad), de_ref) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ layers
+class _NT:
+    """a Lux-style NamedTuple layer `l` (duck typing, GNNLux/src/layers/conv.jl:131-139)"""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def test_gcn_closed_form_and_conv_weight(gnn):
+    # GraphNeuralNetworks/test/layers/conv.jl:30-44
+    s, t = [2, 3, 1, 3, 1, 2], [1, 1, 2, 2, 3, 3]
+    w = torch.tensor([1, 2, 3, 4, 5, 6], dtype=torch.float32)
+    g = gnn.GNNGraph((s, t, w)).cuda()
+    x = gnn.colmajor(torch.ones(1, 3).cuda())
+    l = gnn.GCNConv(1, 1, add_self_loops=False, use_edge_weight=True, device="cuda")
+    with torch.no_grad():
+        l.weight.fill_(1)
+    d = gnn.degree(g, dir="in", edge_weight=True).cpu().numpy()
+    y = l(g, x).detach().cpu().numpy()
+    wn = w.numpy()
+    np.testing.assert_allclose(y[0, 0], wn[0] / np.sqrt(d[0] * d[1]) + wn[1] / np.sqrt(d[0] * d[2]), rtol=1e-6)
+    np.testing.assert_allclose(y[0, 1], wn[2] / np.sqrt(d[1] * d[0]) + wn[3] / np.sqrt(d[1] * d[2]), rtol=1e-6)
+    y2 = l(g, x, w.cuda(), norm_fn=lambda d: 1 / torch.sqrt(d)).detach().cpu().numpy()
+    np.testing.assert_allclose(y, y2, rtol=1e-6)
+    # gradient w.r.t. the edge weights exists and is a vector (conv.jl:47-52)
+    wv = torch.rand(6, device="cuda", requires_grad=True)
+    l(g, gnn.colmajor(torch.rand(1, 3).cuda()), wv).sum().backward()
+    assert wv.grad.shape == (6,) and wv.grad.dtype == torch.float32
+    # conv_weight = 0 => output == 0 == w*x exactly (conv.jl:55-65), on the reference's TEST_GRAPHS
+    adj1 = np.array([[0, 1, 0, 1], [1, 0, 1, 0], [0, 1, 0, 1], [1, 0, 1, 0]])
+    adj2 = np.array([[0, 0, 0, 1], [0, 0, 0, 0], [0, 0, 0, 1], [1, 0, 1, 0]])
+    l = gnn.GCNConv(3, 5, device="cuda")
+    wz = torch.zeros(5, 3, device="cuda")
+    for adj in (adj1, adj2):
+        gg = gnn.GNNGraph(adj).cuda()
+        xx = gnn.colmajor(torch.rand(3, 4).cuda())
+        assert (l(gg, xx, conv_weight=wz) == 0).all()
+        assert l(gg, xx).shape == (5, 4)
+
+
+@pytest.mark.parametrize("din,dout", [(3, 5), (16, 7), (128, 128), (40, 16)])
+@pytest.mark.parametrize("loops", [True, False])
+def test_gcn_conv_parity_and_grad(graph, oracle, gnn, din, dout, loops):
+    name, s, t, n, g = graph
+    if not loops and name != "small":
+        pytest.skip("without self loops isolated nodes give c=Inf (the reference tests skip them too)")
+    rng = np.random.default_rng(din)
+    if not loops:   # make every node a target at least once
+        s = np.concatenate([s, np.arange(1, n + 1)]); t = np.concatenate([t, np.roll(np.arange(1, n + 1), 1)])
+        g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
+    x = rng.standard_normal((n, din)).astype(np.float32)
+    W = (rng.standard_normal((dout, din)) / np.sqrt(din)).astype(np.float32)
+    b = rng.standard_normal(dout).astype(np.float32)
+    l = _NT(weight=torch.as_tensor(W).cuda().requires_grad_(True), bias=torch.as_tensor(b).cuda(), σ=torch.relu,
+            add_self_loops=loops, use_edge_weight=False)
+    xt = jl(x).requires_grad_(True)
+    y = gnn.gcn_conv(l, g, xt)
+    # oracle composition (GNNlib/src/layers/conv.jl:14-72) in fp64
+    s2, t2 = oracle.add_self_loops(s, t, n) if loops else (s, t)
+    x64, W64 = x.astype(np.float64), W.astype(np.float64)
+    h = x64 @ W64.T if dout < din else x64
+    p, c = oracle.gcn_propagate(s2, t2, n, h, None, fused=True)
+    pre = (p @ W64.T if dout >= din else p) + b
+    ref = np.maximum(pre, 0)
+    assert rel(np_rows(y), ref) < 5e-6
+    # gradient of sum(y .* r): dP = c .* A^T-propagate(c .* dPre) etc.
+    r = rng.standard_normal(ref.shape)
+    (y * jl(r.astype(np.float32))).sum().backward()
+    dpre = r * (pre > 0)
+    dp = dpre @ W64 if dout >= din else dpre
+    dh = oracle.propagate_unfused("+", t2, s2, n, dp * c[:, None]) * c[:, None]      # transposed graph
+    dx_ref = dh @ W64 if dout < din else dh
+    dW_ref = dpre.T @ p if dout >= din else dh.T @ x64
+    assert rel(np_rows(xt.grad), dx_ref) < 1e-5
+    assert rel(l.weight.grad.cpu().numpy(), dW_ref) < 1e-5
+
+
+@pytest.mark.parametrize("aggr", ["mean", "+"])
+def test_sage_conv_parity(graph, oracle, gnn, aggr):
+    _, s, t, n, g = graph
+    rng = np.random.default_rng(3)
+    din, dout = 16, 9
+    x = rng.standard_normal((n, din)).astype(np.float32)
+    W = rng.standard_normal((dout, 2 * din)).astype(np.float32) / 4
+    b = rng.standard_normal(dout).astype(np.float32)
+    l = _NT(weight=torch.as_tensor(W).cuda(), bias=torch.as_tensor(b).cuda(), σ=torch.relu,
+            aggr={"mean": gnn.mean, "+": operator.add}[aggr])
+    y = np_rows(gnn.sage_conv(l, g, jl(x)))
+    m = oracle.propagate_unfused(aggr, s, t, n, x.astype(np.float64))
+    ref = np.maximum(np.concatenate([x.astype(np.float64), m], 1) @ W.astype(np.float64).T + b, 0)
+    assert rel(y, ref) < 5e-6
+    mod = gnn.SAGEConv(din, dout, torch.relu, device="cuda")
+    assert mod(g, jl(x)).shape == (dout, n)
+
+
+# ----------------------------------------------------------------------------------- C-ABI host entries
+def test_host_buffer_entries(graph, oracle, gnn):
+    _, s, t, n, g = graph
+    lib = gnn._lib.lib
+    rng = np.random.default_rng(5)
+    D = 32
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    out = np.empty_like(x)
+    gnn._lib.check(lib.gnnb_propagate_host(g.plan().h, 0, gnn._lib.COPY_XJ, gnn._lib.MEAN, x.ctypes.data, None, D,
+                                           out.ctypes.data))
+    assert rel(out, oracle.propagate_unfused("mean", s, t, n, x.astype(np.float64))) < TOL
+    g2 = gnn.add_self_loops(g)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    gnn._lib.check(lib.gnnb_gcn_propagate_host(g2.plan().h, 0, x.ctypes.data, None, D, out.ctypes.data))
+    ref, c = oracle.gcn_propagate(s2, t2, n, x.astype(np.float64))
+    assert rel(out, ref) < TOL
+    gnn._lib.check(lib.gnnb_gcn_propagate_host(g2.plan().h, 1, x.ctypes.data, None, D, out.ctypes.data))
+    ref_t = oracle.propagate_unfused("+", t2, s2, n, x.astype(np.float64) * c[:, None]) * c[:, None]
+    assert rel(out, ref_t) < TOL
+
+
+def test_determinism(graph, gnn):
+    _, s, t, n, g = graph
+    x = gnn.jl_randn(128, n, device="cuda")
+    a = gnn.propagate(gnn.copy_xj, g, operator.add, xj=x)
+    for _ in range(3):
+        assert torch.equal(a, gnn.propagate(gnn.copy_xj, g, operator.add, xj=x))
+
+
+def test_launch_counter(gnn):
+    before = gnn.launch_count()
+    g = gnn.GNNGraph([1, 2, 3], [2, 3, 1]).cuda()
+    gnn.propagate(gnn.copy_xj, g, operator.add, xj=gnn.jl_randn(4, 3, device="cuda"))
+    assert gnn.launch_count() > before
