@@ -86,7 +86,7 @@ _SIGS = {
     "gnnb_gcn_propagate": (_int, [_vp, _int, _f32p, _f32p, _f32p, _i64, _f32p, _vp]),
     "gnnb_gat_aggregate": (_int, [_vp, _f32p, _f32p, _f32p, _i64, _i64, C.c_float, _f32p, _f32p, _f32p,
                                   _f32p, _vp]),
-    "gnnb_gat_aggregate_bwd": (_int, [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, C.c_float,
+    "gnnb_gat_aggregate_bwd": (_int, [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, C.c_float,
                                       _f32p, _f32p, _f32p, _vp]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_gcn_propagate_host": (_int, [_vp, _int, _f32p, _f32p, _i64, _f32p]),

@@ -171,12 +171,12 @@ class _GATAggregateFn(torch.autograd.Function):
                                               Cc, H, slope, out.data_ptr(), None, smax.data_ptr(),
                                               ssum.data_ptr(), _stream(plan.device)))
         ctx.plan, ctx.slope, ctx.dims = plan, slope, (Cc, H)
-        ctx.save_for_backward(Wx_rows, el_rows, er_rows, smax, ssum)
+        ctx.save_for_backward(Wx_rows, el_rows, er_rows, smax, ssum, out)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        Wx_rows, el_rows, er_rows, smax, ssum = ctx.saved_tensors
+        Wx_rows, el_rows, er_rows, smax, ssum, out = ctx.saved_tensors
         Cc, H = ctx.dims
         dout = dout.contiguous()
         dWx = torch.empty_like(Wx_rows)
@@ -185,9 +185,20 @@ class _GATAggregateFn(torch.autograd.Function):
         with torch.cuda.device(ctx.plan.device):
             _lib.check(lib.gnnb_gat_aggregate_bwd(ctx.plan.h, Wx_rows.data_ptr(), el_rows.data_ptr(),
                                                   er_rows.data_ptr(), smax.data_ptr(), ssum.data_ptr(),
-                                                  dout.data_ptr(), Cc, H, ctx.slope, dWx.data_ptr(),
+                                                  out.data_ptr(), dout.data_ptr(), Cc, H, ctx.slope, dWx.data_ptr(),
                                                   del_.data_ptr(), der.data_ptr(), _stream(ctx.plan.device)))
         return dWx, del_, der, None, None
+
+
+def gat_fusable(chout: int, heads: int) -> bool:
+    """Shapes the fused GAT kernels cover (csrc/gat.cu gat_shape): C*H <= 512 with C/4 a power of two <= 32,
+    or C a power of two <= 32 with C*H <= 128.  Everything else takes the reference's own composition."""
+    def pow2(v):
+        return v > 0 and (v & (v - 1)) == 0
+    D = chout * heads
+    if chout % 4 == 0 and pow2(chout // 4) and chout // 4 <= 32 and D <= 512:
+        return True
+    return pow2(chout) and chout <= 32 and D <= 128
 
 
 def gat_message(l, Wxi, Wxj, e):
@@ -229,7 +240,7 @@ def gat_conv(l, g: GNNGraph, x: torch.Tensor, e: Optional[torch.Tensor] = None, 
     Wxi = Wxj
     if xi is not xj:
         Wxi = _jl_reshape3(l.dense_x(xi), chout, heads)
-    if fused and e is None and xi is xj:
+    if fused and e is None and xi is xj and gat_fusable(chout, heads) and float(getattr(l, "dropout", 0.0) or 0.0) == 0.0:
         plan = g.plan()
         Wr = _f32(rows(Wxj), plan.device)                       # (N, H, C)
         a = l.a                                                 # (2C, H)

@@ -176,13 +176,14 @@ int gnnb_gcn_propagate(gnnb_graph_t g, int transposed, const float* x, const flo
 int gnnb_gat_aggregate(gnnb_graph_t g, const float* Wx, const float* el, const float* er,
                        int64_t C, int64_t H, float slope, float* out, float* alpha,
                        float* seg_max, float* seg_sum, void* stream);
-/* pullback: given dout (C,H,num_dst) and the forward statistics, produce
- *   dWx (C,H,num_src) = Σ_{k: s_k=j} α_k dout[:,:,t_k]        (attention-weighted transposed pull)
- *   del (H,num_dst), der (H,num_src): gradients of the two per-node logit terms. */
+/* pullback: given dout (C,H,num_dst), the forward output and the forward statistics, produce
+ *   dWx (C,H,num_src) = Σ_{k: s_k=j} α_k dout[:,:,t_k]        (attention-weighted transposed pull, α recomputed)
+ *   del (H,num_dst), der (H,num_src): gradients of the two per-node logit terms
+ * (the el/er -> a, Wx chain is dense per-node work left to the caller's AD). */
 int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, const float* er,
-                           const float* seg_max, const float* seg_sum, const float* dout,
-                           int64_t C, int64_t H, float slope, float* dWx, float* del, float* der,
-                           void* stream);
+                           const float* seg_max, const float* seg_sum, const float* out_fwd,
+                           const float* dout, int64_t C, int64_t H, float slope, float* dWx, float* del,
+                           float* der, void* stream);
 
 /* ------------------------------------------------------ host-buffer entries
  * The reference-facing call with HOST arrays (what a CPU-array caller of `propagate` has): copies

@@ -461,3 +461,102 @@ def test_launch_counter(gnn):
     g = gnn.GNNGraph([1, 2, 3], [2, 3, 1]).cuda()
     gnn.propagate(gnn.copy_xj, g, operator.add, xj=gnn.jl_randn(4, 3, device="cuda"))
     assert gnn.launch_count() > before
+
+
+# ------------------------------------------------------------------------------------------------- GAT
+def _gat_reference_bwd(oracle, s, t, n, Wx, el, er, dout, slope):
+    """fp64 closed form of the GAT edge part and its pullback."""
+    z = el[t - 1] + er[s - 1]                                   # (E, H)
+    u = np.where(z > 0, z, slope * z)
+    alpha = oracle.softmax_edge_neighbors(t, n, u)
+    out = oracle.scatter("+", alpha[:, :, None] * Wx[s - 1], t, n)
+    dalpha = (dout[t - 1] * Wx[s - 1]).sum(-1)
+    T = oracle.scatter("+", alpha * dalpha, t, n)
+    dz = alpha * (dalpha - T[t - 1]) * np.where(z > 0, 1.0, slope)
+    del_ = oracle.scatter("+", dz, t, n)
+    der = oracle.scatter("+", dz, s, n)
+    dWx = oracle.scatter("+", alpha[:, :, None] * dout[t - 1], s, n)
+    return out, alpha, dWx, del_, der
+
+
+@pytest.mark.parametrize("Cc,H", [(64, 8), (16, 4), (8, 2), (4, 1), (32, 2), (128, 1), (128, 4), (2, 3), (1, 4), (16, 1)])
+def test_gat_aggregate_c_abi(graph, oracle, gnn, Cc, H):
+    name, s, t, n, g = graph
+    if name == "sparse":
+        pytest.skip("GAT always runs with self loops: no empty targets")
+    lib = gnn._lib.lib
+    rng = np.random.default_rng(Cc * 10 + H)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    g2 = gnn.add_self_loops(g)
+    E2 = len(s2)
+    Wx = rng.standard_normal((n, H, Cc)).astype(np.float32)
+    el = rng.standard_normal((n, H)).astype(np.float32)
+    er = rng.standard_normal((n, H)).astype(np.float32)
+    dout = rng.standard_normal((n, H, Cc)).astype(np.float32)
+    slope = 0.2
+    dev = lambda a: torch.as_tensor(a).cuda().contiguous()
+    Wx_d, el_d, er_d, do_d = dev(Wx), dev(el), dev(er), dev(dout)
+    out = torch.empty_like(Wx_d); alpha = torch.empty(E2, H, device="cuda")
+    smax = torch.empty(n, H, device="cuda"); ssum = torch.empty(n, H, device="cuda")
+    p = g2.plan()
+    gnn._lib.check(lib.gnnb_gat_aggregate(p.h, Wx_d.data_ptr(), el_d.data_ptr(), er_d.data_ptr(), Cc, H, slope,
+                                          out.data_ptr(), alpha.data_ptr(), smax.data_ptr(), ssum.data_ptr(), None))
+    f64 = lambda a: a.astype(np.float64)
+    o_ref, a_ref, dWx_ref, del_ref, der_ref = _gat_reference_bwd(oracle, s2, t2, n, f64(Wx), f64(el), f64(er),
+                                                                 f64(dout), slope)
+    assert rel(out.cpu().numpy(), o_ref) < 5e-6
+    assert rel(alpha.cpu().numpy(), a_ref) < 5e-6
+    dWx = torch.empty_like(Wx_d); del_ = torch.empty(n, H, device="cuda"); der = torch.empty(n, H, device="cuda")
+    gnn._lib.check(lib.gnnb_gat_aggregate_bwd(p.h, Wx_d.data_ptr(), el_d.data_ptr(), er_d.data_ptr(), smax.data_ptr(),
+                                              ssum.data_ptr(), out.data_ptr(), do_d.data_ptr(), Cc, H, slope,
+                                              dWx.data_ptr(), del_.data_ptr(), der.data_ptr(), None))
+    assert rel(dWx.cpu().numpy(), dWx_ref) < 1e-5
+    scale = np.linalg.norm(dWx_ref) / np.sqrt(dWx_ref.size) * np.sqrt(Cc)      # dz is a difference of O(1) terms
+    assert np.abs(del_.cpu().numpy() - del_ref).max() < 2e-4 * max(scale, 1)
+    assert np.abs(der.cpu().numpy() - der_ref).max() < 2e-4 * max(scale, 1)
+    assert rel(del_.cpu().numpy(), del_ref) < 2e-4 and rel(der.cpu().numpy(), der_ref) < 2e-4
+
+
+def test_gat_unsupported_shape_is_loud(gnn):
+    g = gnn.GNNGraph([1, 2], [2, 1]).cuda()
+    z = torch.zeros(2, 2, 5, device="cuda")
+    with pytest.raises(gnn.GNNBError):
+        gnn._lib.check(gnn._lib.lib.gnnb_gat_aggregate(g.plan().h, z.data_ptr(), z.data_ptr(), z.data_ptr(), 5, 2, 0.2,
+                                                       z.data_ptr(), None, z.data_ptr(), z.data_ptr(), None))
+
+
+@pytest.mark.parametrize("din,chout", [(3, 5), (8, 16), (16, 64)])
+@pytest.mark.parametrize("heads", [1, 2])
+@pytest.mark.parametrize("concat", [True, False])
+def test_gat_conv_layer(graph, oracle, gnn, din, chout, heads, concat):
+    """GraphNeuralNetworks/test/layers/conv.jl:154-170 (heads x concat sweep): output size, fused == the reference's
+    own composition (generic gather/softmax/scatter path), gradients of both paths agree, forward ≈ fp64 oracle."""
+    name, s, t, n, g = graph
+    if name == "sparse":
+        pytest.skip("covered by the other graphs")
+    torch.manual_seed(0)
+    l = gnn.GATConv(din, chout, torch.relu, heads=heads, concat=concat, device="cuda")
+    with torch.no_grad():
+        l.bias.normal_()
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, din)).astype(np.float32)
+    xa = jl(x).requires_grad_(True)
+    xb = jl(x).requires_grad_(True)
+    ya = l(g, xa)                       # fused when the shape allows, else generic
+    yb = l(g, xb, fused=False)          # the reference's composition
+    assert ya.shape == ((chout * heads) if concat else chout, n)
+    assert rel(ya.detach().cpu(), yb.detach().cpu()) < 1e-5
+    r = jl(rng.standard_normal((n, ya.shape[0])).astype(np.float32))
+    ga = torch.autograd.grad((ya * r).sum(), [xa, l.dense_x.weight, l.a])
+    gb = torch.autograd.grad((yb * r).sum(), [xb, l.dense_x.weight, l.a])
+    for a, b_ in zip(ga, gb):
+        assert rel(a.cpu(), b_.cpu()) < 2e-4
+    # forward against the fp64 oracle (GNNlib/src/layers/conv.jl:112-167 restated)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    W = l.dense_x.weight.detach().cpu().numpy().astype(np.float64)          # (C*H, din)
+    Wx = (x.astype(np.float64) @ W.T).reshape(n, heads, chout)
+    a_rows = l.a.detach().cpu().numpy().astype(np.float64).T                # (H, 2C)
+    o, _ = oracle.gat_aggregate(s2, t2, n, Wx, a_rows, 0.2)
+    o = o.reshape(n, heads * chout) if concat else o.mean(1)
+    ref = np.maximum(o + l.bias.detach().cpu().numpy(), 0)
+    assert rel(np_rows(ya), ref) < 1e-5
