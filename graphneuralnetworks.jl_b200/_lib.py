@@ -88,10 +88,13 @@ _SIGS = {
                                   _f32p, _vp]),
     "gnnb_gat_aggregate_bwd": (_int, [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, C.c_float,
                                       _f32p, _f32p, _f32p, _vp]),
+    "gnnb_gather_rows": (_int, [_vp, _i64, _f32p, _i64, _f32p, _vp]),
+    "gnnb_propagate_halo": (_int, [_vp, _int, _int, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64, _f32p, _vp]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_gcn_propagate_host": (_int, [_vp, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_rmat_edges": (_int, [_i64, _i64, C.c_uint64, _vp, _vp, _vp]),
     "gnnb_set_chunk_edges": (_int, [_int]),
+    "gnnb_set_kernel_variant": (_int, [_int]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

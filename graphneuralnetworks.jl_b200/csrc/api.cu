@@ -92,6 +92,12 @@ int gnnb_device_count(void) {
     return n;
 }
 int64_t gnnb_launch_count(void) { return g_launches.load(); }
+namespace gnnb { extern int g_variant; }
+int gnnb_set_kernel_variant(int v) {
+    if (v < 0 || v > 4) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,4]");
+    gnnb::g_variant = v;
+    return GNNB_OK;
+}
 
 int gnnb_propagate(gnnb_graph_t g, int transposed, int msg, int aggr, const float* x, const float* w,
                    const float* cs, const float* ct, int64_t D, float* out, void* stream) {
@@ -161,6 +167,26 @@ int gnnb_gcn_propagate(gnnb_graph_t g, int transposed, const float* x, const flo
     if (g->n_src != g->n_dst) GNNB_FAIL(GNNB_ESIZE, "gcn_propagate needs num_src == num_dst");
     if (!c) GNNB_FAIL(GNNB_EINVAL, "c (from gnnb_gcn_norm) is NULL");
     return gnnb_propagate(g, transposed, w ? GNNB_W_MUL_XJ : GNNB_COPY_XJ, GNNB_SUM, x, w, c, c, D, out, stream);
+}
+
+// ---- node-partitioned shards ---------------------------------------------------------------------
+int gnnb_propagate_halo(gnnb_graph_t g, int msg, int aggr, const float* x_local, const float* x_halo,
+                        int64_t n_local, const float* w, const float* cs, const float* ct, int64_t D, float* out,
+                        void* stream) {
+    GNNB_TRY(check_common(g, msg, aggr, D, w));
+    if (!out) GNNB_FAIL(GNNB_EINVAL, "out is NULL");
+    if (n_local < 0 || n_local > g->n_src) GNNB_FAIL(GNNB_ESIZE, "n_local must be in [0, num_src]");
+    if (n_local > 0 && !x_local) GNNB_FAIL(GNNB_EINVAL, "x_local is NULL");
+    if (n_local < g->n_src && !x_halo) GNNB_FAIL(GNNB_EINVAL, "x_halo is NULL but the shard has halo sources");
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNB_TRY(ensure_csr(g, false, st));
+    const Csr& c = g->by_dst;
+    SegArgs a;
+    a.x = x_local; a.x2 = x_halo; a.split = (int32_t)n_local;
+    if (!x_local) { a.x = x_halo; a.x2 = nullptr; }   // no local rows at all
+    a.cs = cs; a.ct = ct; a.out = out; a.D = D; a.aggr = aggr;
+    GNNB_TRY(plan_weights(g, c, msg, w, 0, &a.w, st));
+    return seg_reduce(g, c, a, st);
 }
 
 // ---- host-buffer entries ------------------------------------------------------------------------

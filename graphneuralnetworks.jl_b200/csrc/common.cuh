@@ -87,6 +87,8 @@ int ensure_invdeg(gnnb_graph* g, Csr& c, cudaStream_t st);
 // segreduce.cu
 struct SegArgs {
     const float* x = nullptr;   // gathered rows, [ncols][D]
+    const float* x2 = nullptr;  // optional second base for gathered nodes >= split (halo rows)
+    int32_t split = 0;
     const float* w = nullptr;   // per-edge weight in PLAN order or nullptr
     const float* cs = nullptr;  // per gathered-node scale or nullptr
     const float* ct = nullptr;  // per output-row scale or nullptr

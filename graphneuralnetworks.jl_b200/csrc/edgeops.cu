@@ -138,6 +138,18 @@ int gnnb_gather(gnnb_graph_t g, int which, const float* x, int64_t D, float* out
     return GNNB_OK;
 }
 
+int gnnb_gather_rows(const int32_t* idx_dev, int64_t n, const float* x, int64_t D, float* out, void* stream) {
+    if (n < 0 || D <= 0) GNNB_FAIL(GNNB_ESIZE, "gather_rows: bad sizes");
+    if (n == 0) return GNNB_OK;
+    if (!idx_dev || !x || !out) GNNB_FAIL(GNNB_EINVAL, "gather_rows: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool v4 = D % 4 == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15);
+    if (v4) gather_rows_kernel<4><<<nblk(n * (D / 4)), 256, 0, st>>>(idx_dev, n, x, D, out);
+    else gather_rows_kernel<1><<<nblk(n * D), 256, 0, st>>>(idx_dev, n, x, D, out);
+    GNNB_LAUNCHED();
+    return GNNB_OK;
+}
+
 int gnnb_scatter(gnnb_graph_t g, int which, int aggr, const float* m, int64_t D, float* out, void* stream) {
     if (!g) GNNB_FAIL(GNNB_EINVAL, "graph handle is NULL");
     if (aggr < GNNB_SUM || aggr > GNNB_MIN) GNNB_FAIL(GNNB_EINVAL, "unknown aggregation %d", aggr);

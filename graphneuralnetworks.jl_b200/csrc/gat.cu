@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) gat_fwd_kernel(const GatParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t slot = p.D + 2 * (int64_t)p.H;
+    const int64_t slot = (p.D + 2 * (int64_t)p.H + 3) & ~(int64_t)3;   // keep float4 slots 16 B aligned
 
     int64_t foff[K]; bool fact[K]; int head[K]; bool lead[K];
 #pragma unroll
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) gat_fwd_fixup_kernel(const GatParams p, c
     if (li >= n_long) return;
     const int64_t f = (tid % nvec) * VEC;
     const int h = (int)(f / p.C);
-    const int64_t slot = p.D + 2 * (int64_t)p.H;
+    const int64_t slot = (p.D + 2 * (int64_t)p.H + 3) & ~(int64_t)3;   // keep float4 slots 16 B aligned
     const int r = long_rows[li];
     const int rs = p.rowptr[r], re = p.rowptr[r + 1];
     const int k0 = rs / p.chunk, k1 = (re - 1) / p.chunk;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128) gat_bwd_kernel(const GatParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t slot = p.D + (int64_t)p.H;
+    const int64_t slot = (p.D + (int64_t)p.H + 3) & ~(int64_t)3;
     const int L = p.C / VEC;   // lanes per head (power of two <= 32)
 
     int64_t foff[K]; bool fact[K]; int head[K]; bool lead[K];
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256) gat_bwd_fixup_kernel(const GatParams p, c
     if (li >= n_long) return;
     const int64_t f = (tid % nvec) * VEC;
     const int h = (int)(f / p.C);
-    const int64_t slot = p.D + (int64_t)p.H;
+    const int64_t slot = (p.D + (int64_t)p.H + 3) & ~(int64_t)3;
     const int r = long_rows[li];
     const int rs = p.rowptr[r], re = p.rowptr[r + 1];
     const int k0 = rs / p.chunk, k1 = (re - 1) / p.chunk;
@@ -454,7 +454,7 @@ int gnnb_gat_aggregate(gnnb_graph_t g, const float* Wx, const float* el, const f
     p.D = D; p.C = (int32_t)C; p.H = (int32_t)H; p.E = (int32_t)g->E; p.nrows = c.nrows; p.chunk = g->chunk;
     p.nchunks = (int32_t)ceil_div(g->E, g->chunk); p.fill = 1; p.slope = slope;
     if (c.n_long > 0) {
-        GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + 2 * H)));
+        GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + 2 * H + 4)));
         p.ws = g->ws;
     }
     const unsigned grid = (unsigned)ceil_div(p.nchunks, 4);
@@ -518,7 +518,7 @@ int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, con
     p.D = D; p.C = (int32_t)C; p.H = (int32_t)H; p.E = (int32_t)g->E; p.nrows = c.nrows; p.chunk = g->chunk;
     p.nchunks = (int32_t)ceil_div(g->E, g->chunk); p.fill = 1; p.slope = slope;
     if (c.n_long > 0) {
-        GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + H)));
+        GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + H + 4)));
         p.ws = g->ws;
     }
     const unsigned grid = (unsigned)ceil_div(p.nchunks, 4);

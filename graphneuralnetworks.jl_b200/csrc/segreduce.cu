@@ -21,6 +21,7 @@
 // as NNlib's sequential CPU scatter; products are rounded before the add (no FMA contraction) so a
 // short row reproduces the reference's fp32 result bit for bit.
 #include "common.cuh"
+#include "segwalk.cuh"
 #include <math_constants.h>
 #include <math.h>
 
@@ -31,6 +32,7 @@ struct SegParams {
     const int32_t* __restrict__ col;
     const int32_t* __restrict__ row;
     const float* __restrict__ x;
+    const float* __restrict__ x2;   // rows of gathered nodes >= split live here (halo buffer); nullptr = single base
     const float* __restrict__ w;
     const float* __restrict__ cs;
     const float* __restrict__ ct;
@@ -43,6 +45,7 @@ struct SegParams {
     int32_t nchunks;
     int32_t mean;   // divide by the row's edge count at the final store
     int32_t fill;   // 1: groups write the neutral element into the empty rows they pass over
+    int32_t split;  // first gathered-node id served from x2
     float sign;     // +1, or -1 to turn MAX into MIN (min(m) = -max(-m))
 };
 
@@ -113,32 +116,9 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const SegParams p) {
         fact[i] = foff[i] < p.D;
     }
 
-    int e_begin = 0, e_end = 0;
-    bool head_partial = false, tail_partial = false;
-    int prev_row = -1;  // last non-empty row before our first processed edge
-    if (k < p.nchunks) {
-        const int a = (int)(k * C);
-        const int b = (a + C < p.E) ? a + C : p.E;
-        e_begin = a;
-        e_end = b;
-        const int r0 = __ldg(p.row + a);
-        const int rs0 = __ldg(p.rowptr + r0), re0 = __ldg(p.rowptr + r0 + 1);
-        if (rs0 < a) {                    // row r0 began in an earlier chunk
-            if (re0 - rs0 > C) head_partial = true;   // long row: we own the piece [a, ..)
-            else e_begin = re0;                        // short row: its first chunk finishes it
-        }
-        if (e_begin < b) {
-            const int r1 = __ldg(p.row + b - 1);
-            const int rs1 = __ldg(p.rowptr + r1), re1 = __ldg(p.rowptr + r1 + 1);
-            if (re1 > b) {                // last row continues past the chunk
-                if (re1 - rs1 > C) tail_partial = true;  // long: piece [.., b)
-                else e_end = re1;                         // short: overrun and finish it
-            }
-            if (!head_partial) prev_row = (e_begin > 0) ? __ldg(p.row + e_begin - 1) : -1;
-        } else {
-            e_end = e_begin;              // nothing left for this chunk
-        }
-    }
+    const ChunkBounds cb = chunk_bounds(p.rowptr, p.row, k, C, p.E, p.nchunks);   // segwalk.cuh
+    const int e_begin = cb.e_begin, e_end = cb.e_end, prev_row = cb.prev_row;
+    const bool head_partial = cb.head_partial, tail_partial = cb.tail_partial;
     const bool has_work = e_begin < e_end;
 
     V acc[K];
@@ -202,7 +182,8 @@ __global__ void __launch_bounds__(256) seg_reduce_kernel(const SegParams p) {
             for (int u = 0; u < U; ++u) {
                 const int cj = __shfl_sync(FULL, c_l, j0 + u, TPR);
                 const bool valid = (j0 + u) < nb;
-                const float* xr = p.x + (size_t)cj * p.D;
+                const float* xr = (p.x2 != nullptr && cj >= p.split) ? p.x2 + (size_t)(cj - p.split) * p.D
+                                                                     : p.x + (size_t)cj * p.D;
 #pragma unroll
                 for (int i = 0; i < K; ++i)
                     v[u][i] = (valid && fact[i]) ? vld(reinterpret_cast<const V*>(xr + foff[i]))
@@ -299,6 +280,10 @@ static int pow2ceil(int64_t v) {
     return p;
 }
 
+// kernel variant: 0 = register-staged kernel only; v >= 1 = TMA-staged kernel (segbulk.cu) with ring config v-1
+int g_variant = 0;
+int seg_reduce_bulk(const Csr& c, const SegArgs& a, int64_t E, int chunk, float* ws, int fill, int cfg, cudaStream_t st);
+
 int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
     if (a.D <= 0) GNNB_FAIL(GNNB_ESIZE, "feature dimension must be positive (got %lld)", (long long)a.D);
     if (c.nrows == 0) return GNNB_OK;
@@ -312,7 +297,7 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
     }
     SegParams p;
     p.rowptr = c.rowptr; p.col = c.col; p.row = c.row;
-    p.x = a.x; p.w = a.w; p.cs = a.cs; p.ct = a.ct; p.out = a.out;
+    p.x = a.x; p.x2 = a.x2; p.split = a.split; p.w = a.w; p.cs = a.cs; p.ct = a.ct; p.out = a.out;
     p.D = a.D; p.E = (int32_t)g->E; p.nrows = c.nrows; p.chunk = g->chunk;
     p.nchunks = (int32_t)ceil_div(g->E, g->chunk);
     p.mean = (a.aggr == GNNB_MEAN);
@@ -331,9 +316,17 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
         p.ws = g->ws;
     }
     const bool vec4 = (a.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.x2) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     int tpr, k;
-    if (vec4) {
+    int bulk_rc = GNNB_EUNSUPPORTED;
+    if (vec4 && g_variant >= 1) {
+        bulk_rc = seg_reduce_bulk(c, a, g->E, g->chunk, p.ws, p.fill, g_variant - 1, st);
+        if (bulk_rc != GNNB_OK && bulk_rc != GNNB_EUNSUPPORTED) return bulk_rc;
+    }
+    if (bulk_rc == GNNB_OK) {
+        // done by the TMA-staged kernel
+    } else if (vec4) {
         int64_t nv = a.D / 4;
         tpr = (int)(nv >= 32 ? 32 : pow2ceil(nv));
         k = (int)ceil_div(nv, tpr);

@@ -1,0 +1,367 @@
+"""Node-partitioned message passing across the GPUs of one box (the reference has no
+distributed code at all — this is new work prescribed by BASELINE.json's north_star).
+
+Layout: nodes are split into `world` contiguous ranges (cost-balanced: a node costs NODE_COST edge-equivalents
+for the dense per-node work plus its in- and out-degree).  Rank p owns x[:, lo_p:hi_p], every in-edge of its
+nodes (forward shard) and every out-edge of its nodes (backward shard).  One pass =
+
+    pack the rows each peer asked for (gnnb_gather_rows)  ->  one all-to-all-v over NCCL/NVLink
+    ->  ONE fused segmented-reduce kernel over the [local rows | halo rows] source space (gnnb_propagate_halo)
+
+The halo lists are deduplicated per peer (each remote row crosses NVLink once per pass) and built once.
+Both directions are "pull": the backward pass gathers dout rows of remote targets through the backward shard,
+so there is no scatter-reduce across GPUs and every result stays deterministic; inside a target row the
+edges keep their COO order, so a shard reproduces the single-GPU summation order.
+
+`torch.distributed` is plumbing (process group, all_to_all_single); index construction below is plain torch
+ops that also run on CPU tensors with the gloo backend (tests/test_partition_gloo.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import lib
+from .graph import _Plan, _ptr, _stream, rows, unrows
+
+NODE_COST = 16  # dense per-node work (GEMM, bias, relu, grads) in edge-equivalents, from the 1-GPU profile
+
+
+# ---------------------------------------------------------------------------------------------------------
+# index construction (device agnostic)
+# ---------------------------------------------------------------------------------------------------------
+def balanced_bounds(cost: torch.Tensor, world: int) -> List[int]:
+    """contiguous ranges [b[p], b[p+1]) with ~equal total cost."""
+    n = cost.numel()
+    cs = torch.cumsum(cost.to(torch.float64), 0)
+    total = float(cs[-1]) if n else 0.0
+    targets = torch.tensor([total * p / world for p in range(1, world)], dtype=torch.float64, device=cost.device)
+    cuts = torch.searchsorted(cs, targets).tolist() if world > 1 else []
+    b = [0] + [min(max(int(c) + 1, 0), n) for c in cuts] + [n]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
+def build_shard(key0: torch.Tensor, other0: torch.Tensor, lo: int, hi: int, bounds: List[int],
+                self_loops: bool):
+    """Edges whose reduction row `key0` (0-based global) lies in [lo,hi), re-indexed for one GPU.
+
+    Returns dict(row: local reduction row, col: gathered node in [local | halo] space, halo: sorted global ids of
+    the remote gathered nodes, recv_counts: rows expected from every owner)."""
+    sel = (key0 >= lo) & (key0 < hi)
+    k = key0[sel] - lo
+    o = other0[sel]
+    n_local = hi - lo
+    is_local = (o >= lo) & (o < hi)
+    halo = torch.unique(o[~is_local])                       # sorted => grouped by owner (ranges are contiguous)
+    col = torch.where(is_local, o - lo, n_local + torch.searchsorted(halo, o))
+    if self_loops:                                          # (i,i) appended after the originals (transform.jl:17-19)
+        loops = torch.arange(n_local, dtype=k.dtype, device=k.device)
+        k = torch.cat([k, loops])
+        col = torch.cat([col, loops])
+    edges = torch.tensor(bounds[1:], dtype=halo.dtype, device=halo.device)
+    owner = torch.bucketize(halo, edges, right=True)
+    recv_counts = torch.bincount(owner, minlength=len(bounds) - 1).tolist()
+    return {"row": k, "col": col, "halo": halo, "recv_counts": recv_counts, "n_local": n_local}
+
+
+def exchange_requests(halo: torch.Tensor, recv_counts: List[int], lo: int, group=None):
+    """Tell every owner which of its rows this rank needs.  Returns (send_idx int32 local row ids to pack, in peer
+    order; send_counts)."""
+    world = dist.get_world_size(group)
+    dev = halo.device
+    rc = torch.tensor(recv_counts, dtype=torch.int64, device=dev)
+    sc = torch.empty_like(rc)
+    dist.all_to_all_single(sc, rc, group=group)
+    send_counts = sc.tolist()
+    wanted = torch.empty(int(sum(send_counts)), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(wanted, halo.to(torch.int64).contiguous(), output_split_sizes=send_counts,
+                           input_split_sizes=recv_counts, group=group)
+    send_idx = (wanted - lo).to(torch.int32)
+    return send_idx, send_counts
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the distributed graph
+# ---------------------------------------------------------------------------------------------------------
+class _Shard:
+    def __init__(self, d, send_idx, send_counts, plan):
+        self.n_local = d["n_local"]
+        self.n_halo = int(d["halo"].numel())
+        self.recv_counts = d["recv_counts"]
+        self.send_idx = send_idx
+        self.send_counts = send_counts
+        self.plan = plan
+        self.num_edges = int(d["row"].numel())
+
+
+class DistGraph:
+    """A GNNGraph partitioned over the ranks of `group`.  Every rank passes the same global COO (1-based s, t)."""
+
+    def __init__(self, s: torch.Tensor, t: torch.Tensor, num_nodes: int, *, add_self_loops: bool = False,
+                 group=None, device=None, bounds: Optional[List[int]] = None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device) if device is not None else s.device
+        self.num_nodes = int(num_nodes)
+        s0 = s.to(self.device).to(torch.int64) - 1
+        t0 = t.to(self.device).to(torch.int64) - 1
+        if bounds is None:
+            cost = (torch.bincount(t0, minlength=num_nodes) + torch.bincount(s0, minlength=num_nodes) + NODE_COST)
+            bounds = balanced_bounds(cost, self.world)
+        self.bounds = bounds
+        self.lo, self.hi = bounds[self.rank], bounds[self.rank + 1]
+        self.n_local = self.hi - self.lo
+        self.self_loops = add_self_loops
+        self.fwd = self._make(t0, s0, add_self_loops)      # reduce over in-edges of owned targets, gather sources
+        self.bwd = self._make(s0, t0, add_self_loops)      # reduce over out-edges of owned sources, gather targets
+        self._c = None
+
+    def _make(self, key0, other0, loops) -> _Shard:
+        d = build_shard(key0, other0, self.lo, self.hi, self.bounds, loops)
+        send_idx, send_counts = exchange_requests(d["halo"], d["recv_counts"], self.lo, self.group)
+        plan = None
+        if self.device.type == "cuda":
+            h = C.c_void_p()
+            col = d["col"].to(torch.int32).contiguous()
+            row = d["row"].to(torch.int32).contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.gnnb_graph_create(C.byref(h), col.data_ptr(), row.data_ptr(), row.numel(),
+                                                 d["n_local"] + d["halo"].numel(), d["n_local"], 4, 0, 1,
+                                                 _stream(self.device)))
+            plan = _Plan(h.value, self.device)
+        return _Shard(d, send_idx, send_counts, plan)
+
+    # -- halo exchange: rows (n_local, D) -> halo rows (n_halo, D)
+    def halo(self, shard: _Shard, x_rows: torch.Tensor) -> torch.Tensor:
+        D = x_rows.shape[1]
+        n_send = int(shard.send_idx.numel())
+        send = torch.empty((n_send, D), dtype=x_rows.dtype, device=x_rows.device)
+        if x_rows.is_cuda:
+            with torch.cuda.device(self.device):
+                _lib.check(lib.gnnb_gather_rows(shard.send_idx.data_ptr(), n_send, x_rows.data_ptr(), D,
+                                                send.data_ptr(), _stream(self.device)))
+        else:  # gloo/CPU test path for the host logic only
+            send = x_rows[shard.send_idx.long()]
+        recv = torch.empty((shard.n_halo, D), dtype=x_rows.dtype, device=x_rows.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=shard.recv_counts,
+                               input_split_sizes=shard.send_counts, group=self.group)
+        return recv
+
+    def gcn_c(self):
+        """c = 1/sqrt(in-degree) of the owned nodes (exact: rowptr differences of the forward shard), plus the
+        halo copies the two shards need.  Computed once."""
+        if self._c is None:
+            p = self.fwd.plan
+            c = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(lib.gnnb_gcn_norm(p.h, None, c.data_ptr(), _stream(self.device)))
+            cf = torch.cat([c, self.halo(self.fwd, c.reshape(-1, 1)).reshape(-1)])
+            cb = torch.cat([c, self.halo(self.bwd, c.reshape(-1, 1)).reshape(-1)])
+            self._c = (c, cf.contiguous(), cb.contiguous())
+        return self._c
+
+    def propagate(self, shard: _Shard, x_rows: torch.Tensor, cs, ct, aggr=_lib.SUM) -> torch.Tensor:
+        D = x_rows.shape[1]
+        halo = self.halo(shard, x_rows)
+        out = torch.empty_like(x_rows)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.gnnb_propagate_halo(shard.plan.h, _lib.COPY_XJ, aggr, x_rows.data_ptr(),
+                                               halo.data_ptr() if shard.n_halo else None, shard.n_local, None,
+                                               _ptr(cs), _ptr(ct), D, out.data_ptr(), _stream(self.device)))
+        return out
+
+
+class _DistGCNPropagateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_rows, dg: DistGraph):
+        c, cf, cb = dg.gcn_c()
+        ctx.dg = dg
+        return dg.propagate(dg.fwd, x_rows.contiguous(), cf, c)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dg = ctx.dg
+        c, cf, cb = dg.gcn_c()
+        return dg.propagate(dg.bwd, dout.contiguous(), cb, c), None
+
+
+def dist_gcn_conv(l, dg: DistGraph, x_local: torch.Tensor) -> torch.Tensor:
+    """gcn_conv (GNNlib/src/layers/conv.jl:14-72) on the rows this rank owns; x_local is Julia-shaped (Din, n_local).
+    The graph must have been partitioned with add_self_loops = l.add_self_loops.  Weight gradients are per-rank
+    partial sums: all-reduce them like any data-parallel layer."""
+    assert dg.self_loops == bool(l.add_self_loops)
+    W = l.weight
+    Dout, Din = W.shape
+    xr = rows(x_local)
+    if Dout < Din:
+        xr = xr @ W.t()
+    pr = _DistGCNPropagateFn.apply(xr, dg)
+    if Dout >= Din:
+        pr = pr @ W.t()
+    b = getattr(l, "bias", None)
+    if b is not None and b is not False:
+        pr = pr + b
+    sig = getattr(l, "σ", None) or getattr(l, "sigma", None) or (lambda v: v)
+    return unrows(sig(pr))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bench.py --gpus N>1
+# ---------------------------------------------------------------------------------------------------------
+def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks):
+    import gnnb200 as gnn
+    n, E, D = args.nodes, args.edges, args.dim
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    g = gnn.rmat_graph(n, E, seed, device=dev)          # every rank generates the same counter-based edge list
+    dg = DistGraph(g.s, g.t, n, add_self_loops=True, device=dev)
+    dg.gcn_c()
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter() - t0
+    del g
+    torch.cuda.empty_cache()
+
+    torch.manual_seed(0)
+    layer = gnn.GCNConv(D, D, torch.relu, device=dev)   # same seed => same weights on every rank
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = gnn.unrows(torch.randn(dg.n_local, D, device=dev, generator=gen)).requires_grad_(True)
+    dy = gnn.unrows(torch.randn(dg.n_local, D, device=dev, generator=gen))
+
+    def step():
+        x.grad = None
+        layer.weight.grad = None
+        layer.bias.grad = None
+        y = dist_gcn_conv(layer, dg, x)
+        y.backward(dy)
+        dist.all_reduce(layer.weight.grad)
+        dist.all_reduce(layer.bias.grad)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0 = gnn.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clocks:
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    launches = gnn.launch_count() - l0
+
+    # the fused kernel alone on this rank's forward shard (CUDA events on the launch stream), max over ranks
+    c, cf, cb = dg.gcn_c()
+    xr = gnn.rows(x.detach())
+    halo = dg.halo(dg.fwd, xr)
+    out = torch.empty_like(xr)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def kern():
+        _lib.check(lib.gnnb_propagate_halo(dg.fwd.plan.h, _lib.COPY_XJ, _lib.SUM, xr.data_ptr(), halo.data_ptr(),
+                                           dg.n_local, None, cf.data_ptr(), c.data_ptr(), D, out.data_ptr(), st))
+
+    for _ in range(3):
+        kern()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        a.record(); kern(); b.record()
+    torch.cuda.synchronize()
+    kms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    # halo exchange alone
+    for _ in range(2):
+        dg.halo(dg.fwd, xr)
+    torch.cuda.synchronize(); dist.barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        dg.halo(dg.fwd, xr)
+    ev1.record()
+    torch.cuda.synchronize()
+    hms = ev0.elapsed_time(ev1) / args.steps
+    Es = dg.fwd.num_edges
+    alg = Es * (4 * D + 4) + 4 * (dg.n_local + 1) + 4 * D * dg.n_local
+    stats = torch.tensor([kms, hms, float(Es), float(dg.n_local), float(dg.fwd.n_halo), float(dg.bwd.n_halo), alg / (kms * 1e-3) / 1e9],
+                         device=dev, dtype=torch.float64)
+    allst = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(allst, stats)
+    allst = torch.stack(allst).cpu()
+    peak, peak_src = measured_peaks()
+
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(dg.n_local, D, pin_memory=True).normal_()
+        dyh = torch.empty(dg.n_local, D, pin_memory=True).normal_()
+        yh = torch.empty(dg.n_local, D, pin_memory=True)
+        dxh = torch.empty(dg.n_local, D, pin_memory=True)
+
+        def step_host():
+            xd = gnn.unrows(xh.to(dev, non_blocking=True)).requires_grad_(True)
+            layer.weight.grad = None
+            layer.bias.grad = None
+            y = dist_gcn_conv(layer, dg, xd)
+            yh.copy_(gnn.rows(y.detach()), non_blocking=True)
+            y.backward(gnn.unrows(dyh.to(dev, non_blocking=True)))
+            dxh.copy_(gnn.rows(xd.grad), non_blocking=True)
+            dist.all_reduce(layer.weight.grad)
+            return layer.weight.grad.cpu()
+
+        ke = max(2, min(args.steps, 5))
+        step_host()
+        torch.cuda.synchronize(); dist.barrier()
+        ev0.record()
+        for _ in range(ke):
+            step_host()
+        ev1.record()
+        torch.cuda.synchronize()
+        ems = torch.tensor([ev0.elapsed_time(ev1) / ke], device=dev)
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        ems = float(ems)
+        e2e = {"value": E / (ems * 1e-3), "unit": "edges/s", "ms_per_step": ems, "steps": ke,
+               "h2d_bytes_per_step": 2 * 4 * n * D, "d2h_bytes_per_step": 2 * 4 * n * D + 4 * D * D * world,
+               "api": "gnnb200.partition.dist_gcn_conv on pinned host slices (all ranks; bytes are whole-job)"}
+
+    if rank == 0:
+        worst = int(torch.argmax(allst[:, 0]))
+        line = {
+            "metric": "edges/sec fwd+bwd GCNConv 128-dim (RMAT)", "value": E / (ms * 1e-3), "unit": "edges/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"GCNConv {D}->{D} (add_self_loops, relu, bias) fwd+bwd on RMAT N={n} E={E} seed {seed} "
+                                   f"(BASELINE configs[1]), node-partitioned over {world} GPUs, NCCL halo exchange",
+                       "parallelism": f"node-partition x{world}, cost-balanced contiguous ranges",
+                       "l2": "per-GPU features and halo buffers are far larger than the 126 MB L2",
+                       "plan_build_ms": t_plan * 1e3, "chunk_edges": 128,
+                       "per_rank": {"kernel_ms": allst[:, 0].tolist(), "halo_exchange_ms": allst[:, 1].tolist(),
+                                    "shard_edges": allst[:, 2].tolist(), "n_local": allst[:, 3].tolist(),
+                                    "halo_rows_fwd": allst[:, 4].tolist(), "halo_rows_bwd": allst[:, 5].tolist()}},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": float(allst[worst, 6]), "peak": peak, "unit": "GB/s",
+                         "frac": float(allst[worst, 6]) / peak, "traffic": None,
+                         "kernel": "gnnb::seg_reduce_kernel<4,32,1,false> over [local|halo] rows (slowest rank)",
+                         "peak_source": peak_src,
+                         "halo": {"bytes_received_slowest_rank": float(allst[:, 4].max()) * D * 4,
+                                  "ms": float(allst[:, 1].max()),
+                                  "GBps_per_gpu": float(allst[:, 4].max()) * D * 4 / (float(allst[:, 1].max()) * 1e-3) / 1e9,
+                                  "nvlink_peak_GBps": 770.0}},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -185,6 +185,24 @@ int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, con
                            const float* dout, int64_t C, int64_t H, float slope, float* dWx, float* del,
                            float* der, void* stream);
 
+/* ------------------------------------------------- node-partitioned shards
+ * (no reference counterpart: the reference has no distributed code)
+ * A shard is an ordinary plan whose targets are the nodes one GPU owns (num_dst = n_local) and whose
+ * source ids live in the space [local rows | halo rows] (num_src = n_local + n_halo): created with
+ * gnnb_graph_create(..., num_src, num_dst, ...).  The halo rows arrive through one all-to-all-v per pass
+ * (NCCL, driven by the host side: graphneuralnetworks.jl_b200/partition.py).
+ *
+ * gnnb_gather_rows: out[k,:] = x[idx[k],:] for an explicit int32 0-based DEVICE index list — packs the rows
+ * a peer requested into the send buffer. */
+int gnnb_gather_rows(const int32_t* idx_dev, int64_t n, const float* x, int64_t D, float* out,
+                     void* stream);
+/* gnnb_propagate_halo: gnnb_propagate (forward direction of the shard plan) with the gathered rows split
+ * over two buffers: node ids < n_local read x_local, the others read x_halo + (id - n_local)*D.
+ * cs (optional) has num_src entries ([local | halo] order), ct num_dst. */
+int gnnb_propagate_halo(gnnb_graph_t g, int msg, int aggr, const float* x_local, const float* x_halo,
+                        int64_t n_local, const float* w, const float* cs, const float* ct, int64_t D,
+                        float* out, void* stream);
+
 /* ------------------------------------------------------ host-buffer entries
  * The reference-facing call with HOST arrays (what a CPU-array caller of `propagate` has): copies
  * x (and w) to the device, runs the fused pass, copies `out` back; synchronous.  Used for the
@@ -205,6 +223,11 @@ int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t
 /* tuning knob for experiments: edges per work chunk of the segmented-reduce kernels (default 128;
  * power of two in [32, 4096]); affects plans created afterwards. */
 int gnnb_set_chunk_edges(int chunk);
+/* which implementation of the fused segmented reduce runs for fp32 rows of 128/256/512 floats:
+ * 0 = register-staged loads (LDG.128) only; 1..4 = TMA-staged (cp.async.bulk rows into a shared-memory ring,
+ * mbarrier completion) with ring configuration v-1 (stages x warps per CTA: 3x2, 2x3, 3x4, 4x3).
+ * Both produce bit-identical results. */
+int gnnb_set_kernel_variant(int v);
 
 #ifdef __cplusplus
 }

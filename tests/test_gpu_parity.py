@@ -560,3 +560,90 @@ def test_gat_conv_layer(graph, oracle, gnn, din, chout, heads, concat):
     o = o.reshape(n, heads * chout) if concat else o.mean(1)
     ref = np.maximum(o + l.bias.detach().cpu().numpy(), 0)
     assert rel(np_rows(ya), ref) < 1e-5
+
+
+# ------------------------------------------------------------------------ kernel variants and halo addressing
+@pytest.fixture
+def variant(gnn):
+    yield lambda v: gnn._lib.check(gnn._lib.lib.gnnb_set_kernel_variant(v))
+    gnn._lib.lib.gnnb_set_kernel_variant(DEFAULT_VARIANT)
+
+
+DEFAULT_VARIANT = 0
+
+
+@pytest.mark.parametrize("D", [128, 256, 512])
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+def test_tma_staged_variant_is_bit_identical(graph, oracle, gnn, variant, D, aggr):
+    """The cp.async.bulk/mbarrier kernel (segbulk.cu) against the register-staged one: same bits, every ring config."""
+    name, s, t, n, g = graph
+    rng = np.random.default_rng(D)
+    x = jl(rng.standard_normal((n, D)).astype(np.float32))
+    w = torch.as_tensor(rng.random(len(s)).astype(np.float32) + 0.1).cuda()
+    variant(0)
+    base = gnn.propagate(gnn.copy_xj, g, aggr, xj=x)
+    base_w = gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w)
+    assert rel(np_rows(base), oracle.propagate_unfused(aggr, s, t, n, np_rows(x).astype(np.float64))) < TOL
+    for v in (1, 2, 3, 4):
+        variant(v)
+        assert torch.equal(gnn.propagate(gnn.copy_xj, g, aggr, xj=x), base), f"variant {v}"
+        assert torch.equal(gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w), base_w), f"variant {v} weighted"
+
+
+def test_tma_staged_variant_large_chunks(gnn, oracle, variant):
+    """long chunks (many ring wrap-arounds), long rows, GCN scales — both variants, several chunk sizes"""
+    rng = np.random.default_rng(0)
+    n = 3000
+    s, t = make_graph(rng, n, 60000, hubs=2, hub_deg=5000)
+    x = rng.standard_normal((n, 128)).astype(np.float32)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    ref, _ = oracle.gcn_propagate(s2, t2, n, x.astype(np.float64))
+    try:
+        for chunk in (32, 128, 1024, 4096):
+            gnn._lib.check(gnn._lib.lib.gnnb_set_chunk_edges(chunk))
+            g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
+            l = gnn.GCNConv(128, 128, device="cuda")
+            outs = []
+            for v in (0, 1, 3):
+                variant(v)
+                g2 = gnn.add_self_loops(g)
+                c = gnn.layers._gcn_c(g2)
+                out = torch.empty(n, 128, device="cuda")
+                xr = torch.as_tensor(x).cuda()
+                for tr in (0, 1):
+                    gnn._lib.check(gnn._lib.lib.gnnb_gcn_propagate(g2.plan().h, tr, xr.data_ptr(), None, c.data_ptr(), 128,
+                                                                   out.data_ptr(), None))
+                    if tr == 0:
+                        assert rel(out.cpu().numpy(), ref) < TOL, (chunk, v)
+                outs.append(out.clone())
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    finally:
+        gnn._lib.lib.gnnb_set_chunk_edges(128)
+
+
+@pytest.mark.parametrize("D", [5, 16, 128, 256])
+def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
+    """gnnb_propagate_halo: sources < n_local read x_local, the rest x_halo (the [local | halo] space of a shard)."""
+    name, s, t, n, g = graph
+    lib = gnn._lib.lib
+    rng = np.random.default_rng(D)
+    x = torch.as_tensor(rng.standard_normal((n, D)).astype(np.float32)).cuda()
+    n_local = n // 3
+    x_local, x_halo = x[:n_local].clone(), x[n_local:].clone()
+    cs = torch.rand(n, device="cuda") + 0.5
+    ct = torch.rand(n, device="cuda") + 0.5
+    ref = torch.empty_like(x)
+    p = g.plan()
+    for v in (0, 1):
+        variant(v)
+        gnn._lib.check(lib.gnnb_propagate(p.h, 0, gnn._lib.COPY_XJ, gnn._lib.SUM, x.data_ptr(), None, cs.data_ptr(),
+                                          ct.data_ptr(), D, ref.data_ptr(), None))
+        out = torch.empty_like(x)
+        gnn._lib.check(lib.gnnb_propagate_halo(p.h, gnn._lib.COPY_XJ, gnn._lib.SUM, x_local.data_ptr(),
+                                               x_halo.data_ptr(), n_local, None, cs.data_ptr(), ct.data_ptr(), D,
+                                               out.data_ptr(), None))
+        assert torch.equal(out, ref)
+    idx = torch.as_tensor(rng.integers(0, n, 77).astype(np.int32)).cuda()
+    packed = torch.empty(77, D, device="cuda")
+    gnn._lib.check(lib.gnnb_gather_rows(idx.data_ptr(), 77, x.data_ptr(), D, packed.data_ptr(), None))
+    assert torch.equal(packed, x[idx.long()])
