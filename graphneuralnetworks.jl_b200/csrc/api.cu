@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+extern int g_variant;   // segreduce.cu
 int edge_dot(gnnb_graph* g, const float* dout, const float* x, const float* cs, const float* ct, int64_t D,
              float* dw_coo, cudaStream_t st);
 int maxmin_bwd(gnnb_graph* g, const float* w_plan_src, const float* x, const float* dout, const float* out_fwd,
@@ -92,7 +93,6 @@ int gnnb_device_count(void) {
     return n;
 }
 int64_t gnnb_launch_count(void) { return g_launches.load(); }
-namespace gnnb { extern int g_variant; }
 int gnnb_set_kernel_variant(int v) {
     if (v < 0 || v > 4) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,4]");
     gnnb::g_variant = v;
