@@ -49,6 +49,10 @@ struct SegParams {
     float sign;     // +1, or -1 to turn MAX into MIN (min(m) = -max(-m))
 };
 
+// kernel variant: 0 = register-staged kernel; 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu);
+// 5..8 = register-staged kernel with other (loads in flight, occupancy) points
+int g_variant = 0;
+
 template <int VEC> struct VecT;
 template <> struct VecT<4> { using T = float4; };
 template <> struct VecT<1> { using T = float; };
@@ -96,10 +100,11 @@ __device__ __forceinline__ V finish_row(V acc, const SegParams& p, int r) {
     return acc;
 }
 
-template <int VEC, int TPR, int K, bool ISMAX>
-__global__ void __launch_bounds__(256) seg_reduce_kernel(const SegParams p) {
+// UU = row loads a group keeps in flight (0 = default 8/K); MINB = resident CTAs the register allocation must allow
+template <int VEC, int TPR, int K, bool ISMAX, int UU = 0, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) seg_reduce_kernel(const SegParams p) {
     using V = typename VecT<VEC>::T;
-    constexpr int U = (VEC == 4) ? ((8 / K) < TPR ? (8 / K) : TPR) : (8 < TPR ? 8 : TPR);
+    constexpr int U = UU > 0 ? UU : ((VEC == 4) ? ((8 / K) < TPR ? (8 / K) : TPR) : (8 < TPR ? 8 : TPR));
     constexpr unsigned FULL = 0xffffffffu;
     const int lig = threadIdx.x % TPR;                                     // lane in group
     const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / TPR;  // chunk id
@@ -258,6 +263,15 @@ template <int VEC, int TPR, int K, bool ISMAX>
 static int launch_seg(const SegParams& p, cudaStream_t st) {
     const int gpb = 256 / TPR;  // groups per block
     dim3 grid((unsigned)ceil_div(p.nchunks, gpb), (unsigned)ceil_div(p.D, (int64_t)VEC * TPR * K));
+    // experiment knobs for the D=128 fp32 kernel (gnnb_set_kernel_variant 5..8): loads in flight x occupancy
+    if (VEC == 4 && TPR == 32 && K == 1 && g_variant >= 5) {
+        if (g_variant == 5) seg_reduce_kernel<4, 32, 1, ISMAX, 16, 2><<<grid, 256, 0, st>>>(p);
+        else if (g_variant == 6) seg_reduce_kernel<4, 32, 1, ISMAX, 8, 4><<<grid, 256, 0, st>>>(p);
+        else if (g_variant == 7) seg_reduce_kernel<4, 32, 1, ISMAX, 4, 6><<<grid, 256, 0, st>>>(p);
+        else seg_reduce_kernel<4, 32, 1, ISMAX, 32, 1><<<grid, 256, 0, st>>>(p);
+        GNNB_LAUNCHED();
+        return GNNB_OK;
+    }
     seg_reduce_kernel<VEC, TPR, K, ISMAX><<<grid, 256, 0, st>>>(p);
     GNNB_LAUNCHED();
     return GNNB_OK;
@@ -280,8 +294,6 @@ static int pow2ceil(int64_t v) {
     return p;
 }
 
-// kernel variant: 0 = register-staged kernel only; v >= 1 = TMA-staged kernel (segbulk.cu) with ring config v-1
-int g_variant = 0;
 int seg_reduce_bulk(const Csr& c, const SegArgs& a, int64_t E, int chunk, float* ws, int fill, int cfg, cudaStream_t st);
 
 int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
@@ -320,7 +332,7 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
                       ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     int tpr, k;
     int bulk_rc = GNNB_EUNSUPPORTED;
-    if (vec4 && g_variant >= 1) {
+    if (vec4 && g_variant >= 1 && g_variant <= 4) {
         bulk_rc = seg_reduce_bulk(c, a, g->E, g->chunk, p.ws, p.fill, g_variant - 1, st);
         if (bulk_rc != GNNB_OK && bulk_rc != GNNB_EUNSUPPORTED) return bulk_rc;
     }

@@ -15,14 +15,16 @@ dev = torch.device("cuda", 0)
 x = torch.randn(n, D, device=dev)
 out = torch.empty_like(x)
 res = []
-for chunk in (128, 512, 2048):
+CHUNKS = [int(c) for c in os.environ.get('CHUNKS', '128').split(',')]
+VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '0,5,6,7,8').split(',')]
+for chunk in CHUNKS:
     gnn._lib.check(lib.gnnb_set_chunk_edges(chunk))
     g = gnn.rmat_graph(n, E, 17, device=dev)
     g2 = gnn.add_self_loops(g)
     gnn._lib.check(lib.gnnb_graph_csr(g2.plan().h, 1, None, None, None, None))
     c = gnn.layers._gcn_c(g2)
     ref = None
-    for v in (0, 1, 2, 3, 4):
+    for v in VARIANTS:
         gnn._lib.check(lib.gnnb_set_kernel_variant(v))
         row = {"chunk": chunk, "variant": v}
         for tr in (0, 1):
@@ -37,7 +39,7 @@ for chunk in (128, 512, 2048):
             torch.cuda.synchronize()
             row["fwd_ms" if tr == 0 else "bwd_ms"] = sum(a.elapsed_time(b) for a, b in evs) / 5
             if tr == 0:
-                if v == 0:
+                if ref is None:
                     ref = out.clone()
                 else:
                     row["bit_identical_to_v0"] = bool(torch.equal(out, ref))
