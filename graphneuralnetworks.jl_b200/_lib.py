@@ -88,6 +88,10 @@ _SIGS = {
                                   _f32p, _vp]),
     "gnnb_gat_aggregate_bwd": (_int, [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, C.c_float,
                                       _f32p, _f32p, _f32p, _vp]),
+    "gnnb_linear": (_int, [_f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _f32p, _vp]),
+    "gnnb_linear_bwd": (_int, [_f32p, _f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _vp]),
+    "gnnb_dense_set_emulation": (_int, [_int]),
+    "gnnb_dense_emulation_active": (_int, []),
     "gnnb_gather_rows": (_int, [_vp, _i64, _f32p, _i64, _f32p, _vp]),
     "gnnb_propagate_halo": (_int, [_vp, _int, _int, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64, _f32p, _vp]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),

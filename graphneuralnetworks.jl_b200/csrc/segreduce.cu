@@ -49,8 +49,8 @@ struct SegParams {
     float sign;     // +1, or -1 to turn MAX into MIN (min(m) = -max(-m))
 };
 
-// kernel variant: 0 = register-staged kernel; 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu);
-// 5..8 = register-staged kernel with other (loads in flight, occupancy) points
+// kernel variant: 0 = register-staged kernel (default); 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu);
+// 5 = register-staged kernel without the 64-register cap
 int g_variant = 0;
 
 template <int VEC> struct VecT;
@@ -259,147 +259,15 @@ __global__ void fill_empty_rows_kernel(const int32_t* __restrict__ rowptr, float
     if (rowptr[r] == rowptr[r + 1]) out[i] = v;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Rolling-prefetch kernel for wide fp32 rows (D = 128 K floats, one warp per chunk, lane l owns float4 slices
-// l, l+32, ...).  The ncu captures of seg_reduce_kernel showed it latency-bound with ~half of its nominal loads in
-// flight (it issues U row loads, then consumes all U before issuing the next U) and that throughput scales with
-// resident warps, not with loads per warp.  Here a warp keeps U row loads in flight CONTINUOUSLY: slot u of a
-// register ring is refilled with the row of edge j+U right after edge j has been consumed from it, so a consume
-// only waits for its own load.  Few live registers (U*K float4 + accumulators) => 5-6 CTAs of 256 threads per SM.
-// Segment starts come from one ballot per 32-edge batch instead of a shuffle + compare per edge, and the two
-// scales are pre-multiplied per edge.  Same order of additions as seg_reduce_kernel => bit-identical results.
-// ---------------------------------------------------------------------------------------------------------
-template <int K, int U, bool ISMAX, int MINB>
-__global__ void __launch_bounds__(256, MINB) seg_reduce_roll_kernel(const SegParams p) {
-    static_assert(32 % U == 0, "U must divide 32");
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const float neutral = ISMAX ? -CUDART_INF_F : 0.f;
-    const float fillv = ISMAX ? (p.sign < 0.f ? CUDART_INF_F : -CUDART_INF_F) : 0.f;
-    const ChunkBounds cb = chunk_bounds(p.rowptr, p.row, k, p.chunk, p.E, p.nchunks);
-    const int nE = cb.e_end - cb.e_begin;
-    if (nE <= 0) return;                                   // warp-uniform
-    const int nbatch = (nE + 31) >> 5;
-    const int loff = lane * 4;
-
-    float4 acc[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) acc[i] = make_float4(neutral, neutral, neutral, neutral);
-    int r = -1;
-    bool first_flush = true;
-
-    auto flush = [&](int rr, bool last) {
-        float* base;
-        bool raw;
-        if (first_flush && cb.head_partial) { base = p.ws + (size_t)(2 * k + 0) * p.D; raw = true; }
-        else if (last && cb.tail_partial) { base = p.ws + (size_t)(2 * k + 1) * p.D; raw = true; }
-        else { base = p.out + (size_t)rr * p.D; raw = false; }
-        first_flush = false;
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const float4 v = raw ? acc[i] : finish_row<float4>(acc[i], p, rr);
-            *reinterpret_cast<float4*>(base + i * 128 + loff) = v;
-        }
-    };
-    auto fill_gap = [&](int lo, int hi) {
-        if (!p.fill) return;
-        for (int q = lo + 1; q < hi; ++q)
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-                *reinterpret_cast<float4*>(p.out + (size_t)q * p.D + i * 128 + loff) = make_float4(fillv, fillv, fillv, fillv);
-    };
-    // indices / scale of batch b for this lane's edge
-    auto load_idx = [&](int b, int& c, int& d, float& s) {
-        const int my_e = cb.e_begin + b * 32 + lane;
-        c = 0; d = -1; s = 1.f;
-        if (b < nbatch && my_e < cb.e_end) {
-            c = __ldg(p.col + my_e);
-            d = __ldg(p.row + my_e);
-            if (p.cs) s = __ldg(p.cs + c);
-            if (p.w) s = __fmul_rn(s, __ldg(p.w + my_e));
-            if (p.sign < 0.f) s = -s;
-        }
-    };
-    float4 v[U][K];
-    auto issue = [&](int u, int cj, bool valid) {
-        const float* xr = (p.x2 != nullptr && cj >= p.split) ? p.x2 + (size_t)(cj - p.split) * p.D : p.x + (size_t)cj * p.D;
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-            v[u][i] = valid ? __ldg(reinterpret_cast<const float4*>(xr + i * 128 + loff)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-
-    int c_cur, d_cur, c_nxt, d_nxt;
-    float s_cur, s_nxt;
-    load_idx(0, c_cur, d_cur, s_cur);
-    load_idx(1, c_nxt, d_nxt, s_nxt);
-#pragma unroll
-    for (int u = 0; u < U; ++u) issue(u, __shfl_sync(FULL, c_cur, u), u < nE);
-
-    int d_prev = -2;
-#pragma unroll 1
-    for (int b = 0; b < nbatch; ++b) {
-        const int nb = min(32, nE - b * 32);
-        int d_up = __shfl_up_sync(FULL, d_cur, 1);
-        if (lane == 0) d_up = d_prev;
-        const unsigned starts = __ballot_sync(FULL, (lane < nb) && (d_cur != d_up));
-        d_prev = __shfl_sync(FULL, d_cur, nb - 1);
-        const int rest = nE - b * 32;                      // edges from this batch's start to the end of the work
-#pragma unroll 1
-        for (int j0 = 0; j0 < 32; j0 += U) {
-            if (j0 >= nb) break;                           // warp-uniform
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = j0 + u;
-                if (j < nb) {
-                    if ((starts >> j) & 1u) {              // a new row starts at this edge
-                        const int dj = __shfl_sync(FULL, d_cur, j);
-                        if (r >= 0) { flush(r, false); fill_gap(r, dj); }
-                        else if (!cb.head_partial) fill_gap(cb.prev_row, dj);
-                        r = dj;
-#pragma unroll
-                        for (int i = 0; i < K; ++i) acc[i] = make_float4(neutral, neutral, neutral, neutral);
-                    }
-                    const float sj = __shfl_sync(FULL, s_cur, j);
-#pragma unroll
-                    for (int i = 0; i < K; ++i) acc[i] = comb<ISMAX>(acc[i], v[u][i], sj, 1.f);
-                }
-                // refill slot u with the row of edge j+U (this batch or the next one)
-                const int jn = j + U;
-                int cj;
-                if (jn < 32) cj = __shfl_sync(FULL, c_cur, jn);
-                else cj = __shfl_sync(FULL, c_nxt, jn - 32);
-                issue(u, cj, jn < rest);
-            }
-        }
-        c_cur = c_nxt; d_cur = d_nxt; s_cur = s_nxt;
-        load_idx(b + 2, c_nxt, d_nxt, s_nxt);
-    }
-    flush(r, true);
-    if (cb.e_end == p.E) fill_gap(r, p.nrows);
-}
-
-template <int K, int U, int MINB>
-static int launch_roll(const SegParams& p, bool ismax, cudaStream_t st) {
-    const unsigned grid = (unsigned)ceil_div(p.nchunks, 8);
-    if (ismax) seg_reduce_roll_kernel<K, U, true, MINB><<<grid, 256, 0, st>>>(p);
-    else seg_reduce_roll_kernel<K, U, false, MINB><<<grid, 256, 0, st>>>(p);
-    GNNB_LAUNCHED();
-    return GNNB_OK;
-}
-
 template <int VEC, int TPR, int K, bool ISMAX>
 static int launch_seg(const SegParams& p, cudaStream_t st) {
     const int gpb = 256 / TPR;  // groups per block
     dim3 grid((unsigned)ceil_div(p.nchunks, gpb), (unsigned)ceil_div(p.D, (int64_t)VEC * TPR * K));
-    // experiment knobs for the D=128 fp32 kernel (gnnb_set_kernel_variant 5..8): loads in flight x occupancy
-    if (VEC == 4 && TPR == 32 && K == 1 && g_variant >= 5) {
-        if (g_variant == 5) seg_reduce_kernel<4, 32, 1, ISMAX, 8, 5><<<grid, 256, 0, st>>>(p);
-        else if (g_variant == 6) seg_reduce_kernel<4, 32, 1, ISMAX, 8, 4><<<grid, 256, 0, st>>>(p);
-        else if (g_variant == 7) seg_reduce_kernel<4, 32, 1, ISMAX, 4, 6><<<grid, 256, 0, st>>>(p);
-        else if (g_variant == 8) seg_reduce_kernel<4, 32, 1, ISMAX, 4, 8><<<grid, 256, 0, st>>>(p);
-        else if (g_variant == 9) seg_reduce_kernel<4, 32, 1, ISMAX, 2, 8><<<grid, 256, 0, st>>>(p);
-        else seg_reduce_kernel<4, 32, 1, ISMAX, 6, 5><<<grid, 256, 0, st>>>(p);
+    // One warp per 512 B row (D = 128 fp32): throughput follows the number of resident warps, not the loads per warp
+    // (profiles/r1_seg_variants.md): cap the kernel at 64 registers => 4 CTAs x 8 warps per SM.  Variant 5 keeps the
+    // uncapped build (77 registers, 24 warps) for A/B runs.
+    if (VEC == 4 && TPR == 32 && K == 1 && g_variant != 5) {
+        seg_reduce_kernel<4, 32, 1, ISMAX, 8, 4><<<grid, 256, 0, st>>>(p);
         GNNB_LAUNCHED();
         return GNNB_OK;
     }
@@ -467,23 +335,8 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
         bulk_rc = seg_reduce_bulk(c, a, g->E, g->chunk, p.ws, p.fill, g_variant - 1, st);
         if (bulk_rc != GNNB_OK && bulk_rc != GNNB_EUNSUPPORTED) return bulk_rc;
     }
-    if (bulk_rc != GNNB_OK && vec4 && g_variant >= 11 && a.D % 128 == 0 && a.D <= 256) {
-        const int kk = (int)(a.D / 128);
-        if (kk == 1) {
-            if (g_variant == 11) bulk_rc = launch_roll<1, 4, 6>(p, ismax, st);
-            else if (g_variant == 12) bulk_rc = launch_roll<1, 8, 4>(p, ismax, st);
-            else if (g_variant == 13) bulk_rc = launch_roll<1, 4, 8>(p, ismax, st);
-            else if (g_variant == 14) bulk_rc = launch_roll<1, 2, 8>(p, ismax, st);
-            else if (g_variant == 15) bulk_rc = launch_roll<1, 8, 5>(p, ismax, st);
-            else bulk_rc = launch_roll<1, 4, 5>(p, ismax, st);
-        } else {
-            if (g_variant == 12) bulk_rc = launch_roll<2, 4, 4>(p, ismax, st);
-            else bulk_rc = launch_roll<2, 2, 6>(p, ismax, st);
-        }
-        if (bulk_rc != GNNB_OK) return bulk_rc;
-    }
     if (bulk_rc == GNNB_OK) {
-        // done by a wide-row kernel
+        // done by a shared-memory-staged kernel (segbulk.cu)
     } else if (vec4) {
         int64_t nv = a.D / 4;
         tpr = (int)(nv >= 32 ? 32 : pow2ceil(nv));

@@ -61,6 +61,61 @@ def _add_bias(x: torch.Tensor, b) -> torch.Tensor:
     return x + b.reshape(-1, 1)
 
 
+class _LinearFn(torch.autograd.Function):
+    """σ.(W * x .+ b) for σ ∈ {identity, relu} through gnnb_linear / gnnb_linear_bwd (cuBLASLt GEMM with the bias and
+    relu in the epilogue, fp32-emulated on bf16 tensor cores when available; hand-written relu/bias-grad pullback)."""
+
+    @staticmethod
+    def forward(ctx, x_rows, W, bias, relu_flag):
+        N, Din = x_rows.shape
+        Dout = W.shape[0]
+        y = torch.empty((N, Dout), dtype=torch.float32, device=x_rows.device)
+        Wc = W.contiguous()
+        with torch.cuda.device(x_rows.device):
+            _lib.check(lib.gnnb_linear(x_rows.data_ptr(), Wc.data_ptr(), None if bias is None else bias.data_ptr(),
+                                       int(relu_flag), N, Din, Dout, y.data_ptr(), _stream(x_rows.device)))
+        ctx.relu_flag, ctx.has_bias = bool(relu_flag), bias is not None
+        ctx.save_for_backward(x_rows, Wc, y if relu_flag else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_rows, W, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        N, Din = x_rows.shape
+        Dout = W.shape[0]
+        need_dx, need_dW, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x_rows) if need_dx else None
+        dW = torch.empty_like(W) if need_dW else None
+        db = torch.empty(Dout, dtype=torch.float32, device=dy.device) if need_db else None
+        ws = torch.empty_like(dy) if ctx.relu_flag else None
+        p = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(dy.device):
+            _lib.check(lib.gnnb_linear_bwd(dy.data_ptr(), p(y), x_rows.data_ptr(), W.data_ptr(), int(ctx.relu_flag), N, Din,
+                                           Dout, p(ws), p(dx), p(dW), p(db), _stream(dy.device)))
+        return dx, dW, db, None
+
+
+def _is_relu(f) -> bool:
+    return f in (relu, torch.relu, torch.nn.functional.relu)
+
+
+def _linear(l, W: torch.Tensor, x: torch.Tensor, with_bias_act: bool) -> torch.Tensor:
+    """`σ.(W * x .+ b)` (with_bias_act) or `W * x` on Julia-shaped x.  The library GEMM path needs fp32 CUDA tensors,
+    Dout % 4 == 0 and σ ∈ {identity, relu}; anything else is the same arithmetic through torch."""
+    sig = _sigma(l) if with_bias_act else identity
+    b = _bias(l) if with_bias_act else None
+    xr = rows(x)
+    Dout = W.shape[0]
+    fusable = (xr.is_cuda and xr.dtype == torch.float32 and W.dtype == torch.float32 and Dout % 4 == 0 and Dout <= 1024
+               and (sig is identity or _is_relu(sig)) and W.shape[1] % 4 == 0)
+    if fusable:
+        bb = None if b is None else b.contiguous()
+        return unrows(_LinearFn.apply(xr, W, bb, _is_relu(sig)))
+    out = _matmul(W, x)
+    return sig(_add_bias(out, b)) if with_bias_act else out
+
+
 def default_norm_fn(d: torch.Tensor) -> torch.Tensor:
     """d -> 1 ./ sqrt.(d) — GraphNeuralNetworks/src/layers/conv.jl:99."""
     return 1.0 / torch.sqrt(d)
@@ -105,7 +160,7 @@ def gcn_conv(l, g: GNNGraph, x: torch.Tensor, edge_weight: Optional[torch.Tensor
             assert edge_weight.numel() == g.num_edges
     Dout, Din = weight.shape
     if Dout < Din:
-        x = _matmul(weight, x)  # multiply before convolution if it is more convenient
+        x = _linear(l, weight, x, False)  # multiply before convolution if it is more convenient
     xj, xi = expand_srcdst(g, x)
     check_num_nodes(g, xj)
     use_w = bool(getattr(l, "use_edge_weight", False)) and g.w is not None
@@ -128,7 +183,7 @@ def gcn_conv(l, g: GNNGraph, x: torch.Tensor, edge_weight: Optional[torch.Tensor
             out = propagate(copy_xj, g, operator.add, xj=xs)
         out = out * c.reshape(1, -1)
     if Dout >= Din:
-        out = _matmul(weight, out)
+        return _linear(l, weight, out, True)      # σ.(W * x .+ b): one GEMM with the bias/relu epilogue
     return _sigma(l)(_add_bias(out, _bias(l)))
 
 

@@ -185,6 +185,24 @@ int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, con
                            const float* dout, int64_t C, int64_t H, float slope, float* dWx, float* del,
                            float* der, void* stream);
 
+/* ------------------------------------------------------- dense layer part
+ * replaces: l.σ.(weight * x .+ l.bias) of the conv layers (GNNlib/src/layers/conv.jl:39,69-71; :281) and its pullback.
+ * A plain library GEMM like the reference's (BLAS/cuBLAS sgemm), issued through cuBLASLt 12.9 with the fp32-emulated
+ * compute type (3 x bf16 split, bf16 tensor cores, fp32 accumulate; SIMT sgemm if unavailable), bias (+relu) in the
+ * epilogue.  x (Din,N), W (Dout,Din) row-major as the layer stores it, bias NULL or Dout floats, y (Dout,N).
+ * relu: 0 = identity, 1 = relu. */
+int gnnb_linear(const float* x, const float* W, const float* bias, int relu, int64_t N, int64_t Din,
+                int64_t Dout, float* y, void* stream);
+/* pullback: dy (Dout,N); y = forward output (relu only); dpre_ws = (Dout,N) workspace (relu only);
+ * outputs (each may be NULL): dx (Din,N), dW (Dout,Din), db (Dout).  The relu mask x upstream gradient and the bias
+ * gradient are one hand-written pass (deterministic two-stage column sum). */
+int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, int relu, int64_t N,
+                    int64_t Din, int64_t Dout, float* dpre_ws, float* dx, float* dW, float* db, void* stream);
+/* 1 (default) = try the fp32-emulated tensor-core GEMM; 0 = force the SIMT sgemm.  *_active: -1 not yet used,
+ * 0 unavailable / off, 1 in use. */
+int gnnb_dense_set_emulation(int on);
+int gnnb_dense_emulation_active(void);
+
 /* ------------------------------------------------- node-partitioned shards
  * (no reference counterpart: the reference has no distributed code)
  * A shard is an ordinary plan whose targets are the nodes one GPU owns (num_dst = n_local) and whose
@@ -223,10 +241,11 @@ int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t
 /* tuning knob for experiments: edges per work chunk of the segmented-reduce kernels (default 128;
  * power of two in [32, 4096]); affects plans created afterwards. */
 int gnnb_set_chunk_edges(int chunk);
-/* which implementation of the fused segmented reduce runs for fp32 rows of 128/256/512 floats:
- * 0 = register-staged loads (LDG.128) only; 1..4 = TMA-staged (cp.async.bulk rows into a shared-memory ring,
- * mbarrier completion) with ring configuration v-1 (stages x warps per CTA: 3x2, 2x3, 3x4, 4x3).
- * Both produce bit-identical results. */
+/* A/B switch for the fused segmented reduce on fp32 rows of 128/256/512 floats (results are bit-identical):
+ * 0 = register-staged LDG.128 kernel, capped at 64 registers for 32 resident warps/SM (default, fastest measured);
+ * 1 = TMA-staged: one cp.async.bulk (UBLKCP) per row into a shared-memory ring, mbarrier completion;
+ * 2..4 = cp.async (LDGSTS) rings of 64/32/16 rows per warp;  5 = register-staged kernel without the register cap.
+ * Measurements: profiles/r1_seg_variants.md. */
 int gnnb_set_kernel_variant(int v);
 
 #ifdef __cplusplus

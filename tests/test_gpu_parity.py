@@ -584,7 +584,7 @@ def test_tma_staged_variant_is_bit_identical(graph, oracle, gnn, variant, D, agg
     base = gnn.propagate(gnn.copy_xj, g, aggr, xj=x)
     base_w = gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w)
     assert rel(np_rows(base), oracle.propagate_unfused(aggr, s, t, n, np_rows(x).astype(np.float64))) < TOL
-    for v in (1, 2, 3, 4, 6, 9, 11, 12, 13, 14, 15, 16):
+    for v in (1, 2, 3, 4, 5):
         variant(v)
         assert torch.equal(gnn.propagate(gnn.copy_xj, g, aggr, xj=x), base), f"variant {v}"
         assert torch.equal(gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w), base_w), f"variant {v} weighted"
@@ -604,7 +604,7 @@ def test_tma_staged_variant_large_chunks(gnn, oracle, variant):
             g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
             l = gnn.GCNConv(128, 128, device="cuda")
             outs = []
-            for v in (0, 1, 3, 11, 12):
+            for v in (0, 1, 3, 5):
                 variant(v)
                 g2 = gnn.add_self_loops(g)
                 c = gnn.layers._gcn_c(g2)
@@ -634,7 +634,7 @@ def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
     ct = torch.rand(n, device="cuda") + 0.5
     ref = torch.empty_like(x)
     p = g.plan()
-    for v in (0, 1, 11):
+    for v in (0, 1, 5):
         variant(v)
         gnn._lib.check(lib.gnnb_propagate(p.h, 0, gnn._lib.COPY_XJ, gnn._lib.SUM, x.data_ptr(), None, cs.data_ptr(),
                                           ct.data_ptr(), D, ref.data_ptr(), None))
@@ -647,3 +647,40 @@ def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
     packed = torch.empty(77, D, device="cuda")
     gnn._lib.check(lib.gnnb_gather_rows(idx.data_ptr(), 77, x.data_ptr(), D, packed.data_ptr(), None))
     assert torch.equal(packed, x[idx.long()])
+
+
+# --------------------------------------------------------------------------------------------- dense layer part
+@pytest.mark.parametrize("N,Din,Dout", [(1000, 128, 128), (777, 16, 8), (5000, 64, 256), (33, 1432, 16), (0, 8, 8)])
+@pytest.mark.parametrize("relu_flag,with_bias", [(1, True), (0, True), (1, False), (0, False)])
+@pytest.mark.parametrize("emulate", [1, 0])
+def test_linear_c_abi(gnn, N, Din, Dout, relu_flag, with_bias, emulate):
+    """gnnb_linear / gnnb_linear_bwd (σ.(W*x .+ b), conv.jl:69-71) against fp64: the fp32-emulated tensor-core GEMM must
+    stay inside the 1e-5 bar, like the SIMT sgemm."""
+    lib = gnn._lib.lib
+    lib.gnnb_dense_set_emulation(emulate)
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(N + Din)
+        x = torch.randn(N, Din, device="cuda", generator=gen)
+        W = torch.randn(Dout, Din, device="cuda", generator=gen) / Din ** 0.5
+        b = torch.randn(Dout, device="cuda", generator=gen) if with_bias else None
+        dy = torch.randn(N, Dout, device="cuda", generator=gen)
+        y = torch.empty(N, Dout, device="cuda")
+        gnn._lib.check(lib.gnnb_linear(x.data_ptr(), W.data_ptr(), None if b is None else b.data_ptr(), relu_flag, N, Din,
+                                       Dout, y.data_ptr(), None))
+        pre = x.double() @ W.double().t() + (0 if b is None else b.double())
+        ref = pre.clamp(min=0) if relu_flag else pre
+        if N:
+            assert rel(y.cpu(), ref.cpu()) < 5e-6
+        ws = torch.empty_like(dy); dx = torch.empty_like(x); dW = torch.empty_like(W); db = torch.empty(Dout, device="cuda")
+        gnn._lib.check(lib.gnnb_linear_bwd(dy.data_ptr(), y.data_ptr(), x.data_ptr(), W.data_ptr(), relu_flag, N, Din, Dout,
+                                           ws.data_ptr(), dx.data_ptr(), dW.data_ptr(), db.data_ptr(), None))
+        dpre = dy.double() * (y > 0) if relu_flag else dy.double()
+        if N:
+            assert rel(dx.cpu(), (dpre @ W.double()).cpu()) < 5e-6
+            assert rel(dW.cpu(), (dpre.t() @ x.double()).cpu()) < 5e-6
+            assert rel(db.cpu(), dpre.sum(0).cpu()) < 5e-6
+        else:
+            assert (db == 0).all()
+        assert lib.gnnb_dense_emulation_active() in (0, 1)
+    finally:
+        lib.gnnb_dense_set_emulation(1)
