@@ -65,6 +65,7 @@ static int matmul(cublasOperation_t ta, cublasOperation_t tb, int64_t m, int64_t
                   const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, int relu, cudaStream_t st) {
     GNNB_TRY(load());
     if (m == 0 || n == 0) return GNNB_OK;
+    if (k == 0 && ldc == m && !bias) { GNNB_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)(m * n), st)); return GNNB_OK; }
     const bool try_emu = want_emulation && emulation != 0;
     for (int pass = try_emu ? 0 : 1; pass < 2; ++pass) {
         const bool emu = (pass == 0);
