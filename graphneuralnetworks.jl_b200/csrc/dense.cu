@@ -166,23 +166,31 @@ int gnnb_dense_emulation_active(void) { return lt::emulation; }
 
 int gnnb_linear(const float* x, const float* W, const float* bias, int relu, int64_t N, int64_t Din, int64_t Dout,
                 float* y, void* stream) {
-    if (!x || !W || !y) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
     if (N < 0 || Din <= 0 || Dout <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
+    if (N == 0) return GNNB_OK;
+    if (!x || !W || !y) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
     // column-major: Y(Dout x N) = W(Dout x Din) X(Din x N); W is stored (Dout, Din) row-major = col-major (Din x Dout)
     return lt::matmul(CUBLAS_OP_T, CUBLAS_OP_N, Dout, N, Din, W, Din, x, Din, y, Dout, bias, relu, (cudaStream_t)stream);
 }
 
 int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, int relu, int64_t N, int64_t Din,
                     int64_t Dout, float* dpre_ws, float* dx, float* dW, float* db, void* stream) {
-    if (!dy || !W) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
-    if (relu && (!y || !dpre_ws)) GNNB_FAIL(GNNB_EINVAL, "relu pullback needs the forward output and a (N,Dout) workspace");
     if (N < 0 || Din <= 0 || Dout <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) {   // empty batch: zero parameter gradients, nothing else to do
+        if (dW) GNNB_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)(Din * Dout), st));
+        if (db) GNNB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Dout, st));
+        return GNNB_OK;
+    }
+    if (!dy || !W) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
+    if (relu && (!y || !dpre_ws)) GNNB_FAIL(GNNB_EINVAL, "relu pullback needs the forward output and a (N,Dout) workspace");
     const float* dpre = dy;
     if ((relu || db) && N > 0) {
         if (Dout % 4 != 0 || Dout > 1024 || ((uintptr_t)dy & 15) || (relu && (((uintptr_t)y & 15) || ((uintptr_t)dpre_ws & 15))))
             GNNB_FAIL(GNNB_EUNSUPPORTED, "linear_bwd: Dout must be a multiple of 4 (<= 1024) and pointers 16 B aligned");
-        const int rows_per_block = 512;
+        // about 8 CTAs per SM worth of blocks: long row runs per block keep the deterministic final pass short
+        int64_t rpb = ceil_div(N, 148 * 8);
+        const int rows_per_block = (int)(rpb < 64 ? 64 : rpb);
         const int nblocks = (int)ceil_div(N, rows_per_block);
         float* partial = nullptr;
         if (db) {
