@@ -684,3 +684,36 @@ def test_linear_c_abi(gnn, N, Din, Dout, relu_flag, with_bias, emulate):
         assert lib.gnnb_dense_emulation_active() in (0, 1)
     finally:
         lib.gnnb_dense_set_emulation(1)
+
+
+# ---------------------------------------------------------------------------------- full-size properties (config 2)
+def test_full_size_properties(gnn):
+    """BASELINE configs[1] sizes (RMAT N=10M, E=100M, D=128): size-independent properties instead of an oracle run —
+    propagate(ones) == in-degree exactly (integers are exact in fp32), GCN normalisation of ones, linearity, and
+    <A x, y> == <x, A^T y> between the forward and the transposed plan."""
+    n, E, D = 10_000_000, 100_000_000, 128
+    g = gnn.rmat_graph(n, E, 17)
+    deg = gnn.degree(g, torch.float32, dir="in")
+    assert float(deg.sum()) == E                                   # checksum of the whole edge list
+    ones = gnn.unrows(torch.ones(n, 8, device="cuda"))
+    out = gnn.propagate(gnn.copy_xj, g, operator.add, xj=ones)
+    assert torch.equal(gnn.rows(out)[:, 0], deg) and torch.equal(gnn.rows(out)[:, 7], deg)
+    m = gnn.propagate(gnn.copy_xj, g, gnn.mean, xj=ones)
+    assert torch.equal(gnn.rows(m)[:, 0], (deg > 0).float())       # mean of ones is 1 where there are in-edges, else 0
+    del ones, out, m
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, D, device="cuda", generator=gen)
+    y = torch.randn(n, D, device="cuda", generator=gen)
+    px = gnn.rows(gnn.propagate(gnn.copy_xj, g, operator.add, xj=gnn.unrows(x)))
+    # linearity: P(2x + y) == 2 P(x) + P(y) up to rounding
+    py = gnn.rows(gnn.propagate(gnn.copy_xj, g, operator.add, xj=gnn.unrows(y)))
+    pz = gnn.rows(gnn.propagate(gnn.copy_xj, g, operator.add, xj=gnn.unrows(2 * x + y)))
+    assert float((pz - (2 * px + py)).norm() / pz.norm()) < 1e-6
+    del py, pz
+    # adjointness between the two plans: <P x, y> == <x, P^T y>
+    lib = gnn._lib.lib
+    pty = torch.empty_like(x)
+    gnn._lib.check(lib.gnnb_propagate(g.plan().h, 1, gnn._lib.COPY_XJ, gnn._lib.SUM, y.data_ptr(), None, None, None, D,
+                                      pty.data_ptr(), None))
+    a = float((px.double() * y.double()).sum()); b = float((x.double() * pty.double()).sum())
+    assert abs(a - b) <= 1e-6 * max(abs(a), abs(b), 1.0)
