@@ -293,16 +293,32 @@ def run_ours(args):
         yh = torch.empty(n, D, pin_memory=True)
         dxh = torch.empty(n, D, pin_memory=True)
 
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+
         def step_host():
-            xd = gnn.unrows(xh.to(dev, non_blocking=True)).requires_grad_(True)
+            # PCIe is full duplex: uploads ride stream s_in, downloads s_out, compute the main stream
+            with torch.cuda.stream(s_in):
+                xd_raw = xh.to(dev, non_blocking=True)
+                ev_x = torch.cuda.Event(); ev_x.record(s_in)
+                dyd_raw = dyh.to(dev, non_blocking=True)
+                ev_dy = torch.cuda.Event(); ev_dy.record(s_in)
+            main.wait_event(ev_x)
+            xd = gnn.unrows(xd_raw).requires_grad_(True)
             y = layer(g, xd)
-            yh.copy_(gnn.rows(y.detach()), non_blocking=True)
-            dyd = gnn.unrows(dyh.to(dev, non_blocking=True))
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                yh.copy_(gnn.rows(y.detach()), non_blocking=True)
+            main.wait_event(ev_dy)
             layer.weight.grad = None
             layer.bias.grad = None
-            y.backward(dyd)
-            dxh.copy_(gnn.rows(xd.grad), non_blocking=True)
-            wg = layer.weight.grad.cpu()   # D2H read of the step's result (synchronises)
+            y.backward(gnn.unrows(dyd_raw))
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                dxh.copy_(gnn.rows(xd.grad), non_blocking=True)
+            wg = layer.weight.grad.cpu()   # D2H read of the step's result (synchronises the main stream)
+            main.wait_stream(s_out)
+            xd_raw.record_stream(main); dyd_raw.record_stream(main)
             return wg
 
         ke = max(2, min(args.steps, 5))

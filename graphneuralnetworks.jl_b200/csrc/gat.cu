@@ -73,18 +73,19 @@ __device__ __forceinline__ void gst(float* p, float v) { *p = v; }
 // ------------------------------------------------------------------------------------------------ forward
 // partial slot layout (floats): [acc: D][M: H][S: H]
 template <int VEC, int K>
-__global__ void __launch_bounds__(128) gat_fwd_kernel(const GatParams p) {
+__global__ void __launch_bounds__(128, (K == 1 ? 8 : 1)) gat_fwd_kernel(const GatParams p) {
     using V = typename GV<VEC>::T;
-    constexpr int U = (K >= 4) ? 2 : (K == 2 ? 4 : 8);
+    constexpr int U = (K >= 4) ? 2 : 4;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t slot = (p.D + 2 * (int64_t)p.H + 3) & ~(int64_t)3;   // keep float4 slots 16 B aligned
+    const int64_t d0 = (int64_t)blockIdx.y * (32 * VEC * K);           // feature tile (whole heads per tile)
 
     int64_t foff[K]; bool fact[K]; int head[K]; bool lead[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        foff[i] = (int64_t)(i * 32 + lane) * VEC;
+        foff[i] = d0 + (int64_t)(i * 32 + lane) * VEC;
         fact[i] = foff[i] < p.D;
         head[i] = fact[i] ? (int)(foff[i] / p.C) : 0;
         lead[i] = fact[i] && (foff[i] % p.C == 0);
@@ -229,7 +230,7 @@ __global__ void gat_alpha_kernel(const int32_t* __restrict__ s, const int32_t* _
 }
 
 // T[i,h] = <dout[i,h,:], out[i,h,:]>   (= Σ_k α_k dα_k)
-template <int VEC, int K>
+template <int VEC>
 __global__ void __launch_bounds__(256) gat_tnode_kernel(const float* __restrict__ dout, const float* __restrict__ outf,
                                                         int64_t n, int64_t D, int C, int H, float* __restrict__ T) {
     using V = typename GV<VEC>::T;
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(256) gat_tnode_kernel(const float* __restrict_
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n) return;
     const int L = C / VEC;
-#pragma unroll
-    for (int q = 0; q < K; ++q) {
+    const int nslice = (int)((D / VEC + 31) / 32);
+    for (int q = 0; q < nslice; ++q) {
         const int64_t f = (int64_t)(q * 32 + lane) * VEC;
         float d = 0.f;
         if (f < D) d = gdot(gld(reinterpret_cast<const V*>(dout + i * D + f)), gld(reinterpret_cast<const V*>(outf + i * D + f)));
@@ -250,19 +251,20 @@ __global__ void __launch_bounds__(256) gat_tnode_kernel(const float* __restrict_
 // ----------------------------------------------------------------------------------------------- backward
 // CSR-by-source: row j = source node; col = target i.  partial slot layout: [acc: D][der: H]
 template <int VEC, int K>
-__global__ void __launch_bounds__(128) gat_bwd_kernel(const GatParams p) {
+__global__ void __launch_bounds__(128, (K == 1 ? 5 : 1)) gat_bwd_kernel(const GatParams p) {
     using V = typename GV<VEC>::T;
-    constexpr int U = (K >= 4) ? 2 : (K == 2 ? 4 : 8);
+    constexpr int U = (K >= 4) ? 2 : 4;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t slot = (p.D + (int64_t)p.H + 3) & ~(int64_t)3;
     const int L = p.C / VEC;   // lanes per head (power of two <= 32)
+    const int64_t d0 = (int64_t)blockIdx.y * (32 * VEC * K);
 
     int64_t foff[K]; bool fact[K]; int head[K]; bool lead[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        foff[i] = (int64_t)(i * 32 + lane) * VEC;
+        foff[i] = d0 + (int64_t)(i * 32 + lane) * VEC;
         fact[i] = foff[i] < p.D;
         head[i] = fact[i] ? (int)(foff[i] / p.C) : 0;
         lead[i] = fact[i] && (foff[i] % p.C == 0);
@@ -395,13 +397,14 @@ __global__ void gat_zero_kernel(float* a, int64_t n) {
     if (i < n) a[i] = 0.f;
 }
 
-// shapes the fused kernels cover: D = C*H <= 512 floats (vec4) or <= 128 (scalar), C/VEC a power of two <= 32
+// shapes the fused kernels cover: vec4: C/4 a power of two <= 32 (C | 128, so a 128-float tile holds whole heads; any H,
+// grid.y tiles the row); scalar: C a power of two <= 32 with C*H <= 128
 static bool gat_shape(int64_t C, int64_t H, const void* a, const void* b, int* vec, int* kk) {
     const int64_t D = C * H;
     auto pow2 = [](int64_t v) { return v > 0 && (v & (v - 1)) == 0; };
     const bool aligned = !((uintptr_t)a & 15) && !((uintptr_t)b & 15);
-    if (C % 4 == 0 && aligned && pow2(C / 4) && C / 4 <= 32 && D <= 512) {
-        *vec = 4; int64_t nv = D / 4; int k = (int)ceil_div(nv, 32); *kk = k <= 1 ? 1 : (k == 2 ? 2 : 4);
+    if (C % 4 == 0 && aligned && pow2(C / 4) && C / 4 <= 32) {
+        *vec = 4; *kk = 1;
         return true;
     }
     if (pow2(C) && C <= 32 && D <= 128) {
@@ -418,9 +421,7 @@ static inline unsigned nblk(int64_t n) { return (unsigned)ceil_div(n, 256); }
 
 #define GAT_DISPATCH(KERNEL, vec, kk, grid, st, p)                                            \
     do {                                                                                      \
-        if (vec == 4 && kk == 1) KERNEL<4, 1><<<grid, 128, 0, st>>>(p);                       \
-        else if (vec == 4 && kk == 2) KERNEL<4, 2><<<grid, 128, 0, st>>>(p);                  \
-        else if (vec == 4) KERNEL<4, 4><<<grid, 128, 0, st>>>(p);                             \
+        if (vec == 4) KERNEL<4, 1><<<grid, 128, 0, st>>>(p);                                  \
         else if (kk == 1) KERNEL<1, 1><<<grid, 128, 0, st>>>(p);                              \
         else if (kk == 2) KERNEL<1, 2><<<grid, 128, 0, st>>>(p);                              \
         else KERNEL<1, 4><<<grid, 128, 0, st>>>(p);                                           \
@@ -457,7 +458,7 @@ int gnnb_gat_aggregate(gnnb_graph_t g, const float* Wx, const float* el, const f
         GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + 2 * H + 4)));
         p.ws = g->ws;
     }
-    const unsigned grid = (unsigned)ceil_div(p.nchunks, 4);
+    const dim3 grid((unsigned)ceil_div(p.nchunks, 4), (unsigned)ceil_div(D, (int64_t)32 * vec * kk));
     GAT_DISPATCH(gat_fwd_kernel, vec, kk, grid, st, p);
     GNNB_LAUNCHED();
     if (c.n_long > 0) {
@@ -503,12 +504,8 @@ int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, con
     float* dz = g->ws2 + (size_t)n_dst * H;
     {
         const unsigned tb = nblk(n_dst * 32);
-        if (vec == 4 && kk == 1) gat_tnode_kernel<4, 1><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
-        else if (vec == 4 && kk == 2) gat_tnode_kernel<4, 2><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
-        else if (vec == 4) gat_tnode_kernel<4, 4><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
-        else if (kk == 1) gat_tnode_kernel<1, 1><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
-        else if (kk == 2) gat_tnode_kernel<1, 2><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
-        else gat_tnode_kernel<1, 4><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
+        if (vec == 4) gat_tnode_kernel<4><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
+        else gat_tnode_kernel<1><<<tb, 256, 0, st>>>(dout, out_fwd, n_dst, D, (int)C, (int)H, T);
         GNNB_LAUNCHED();
     }
     GatParams p = {};
@@ -521,7 +518,7 @@ int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, con
         GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + H + 4)));
         p.ws = g->ws;
     }
-    const unsigned grid = (unsigned)ceil_div(p.nchunks, 4);
+    const dim3 grid((unsigned)ceil_div(p.nchunks, 4), (unsigned)ceil_div(D, (int64_t)32 * vec * kk));
     GAT_DISPATCH(gat_bwd_kernel, vec, kk, grid, st, p);
     GNNB_LAUNCHED();
     if (c.n_long > 0) {

@@ -246,14 +246,13 @@ class _GATAggregateFn(torch.autograd.Function):
 
 
 def gat_fusable(chout: int, heads: int) -> bool:
-    """Shapes the fused GAT kernels cover (csrc/gat.cu gat_shape): C*H <= 512 with C/4 a power of two <= 32,
-    or C a power of two <= 32 with C*H <= 128.  Everything else takes the reference's own composition."""
+    """Shapes the fused GAT kernels cover (csrc/gat.cu gat_shape): C/4 a power of two <= 32 (any number of heads), or
+    C a power of two <= 32 with C*H <= 128.  Everything else takes the reference's own composition."""
     def pow2(v):
         return v > 0 and (v & (v - 1)) == 0
-    D = chout * heads
-    if chout % 4 == 0 and pow2(chout // 4) and chout // 4 <= 32 and D <= 512:
+    if chout % 4 == 0 and pow2(chout // 4) and chout // 4 <= 32:
         return True
-    return pow2(chout) and chout <= 32 and D <= 128
+    return pow2(chout) and chout <= 32 and chout * heads <= 128
 
 
 def gat_message(l, Wxi, Wxj, e):
@@ -325,7 +324,7 @@ class _Dense(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros(ch_out, device=device)) if bias else None
 
     def forward(self, x):
-        return _add_bias(_matmul(self.weight, x), self.bias)
+        return _linear(self, self.weight, x, True)     # W * x .+ b (σ = identity)
 
 
 class GATConv(torch.nn.Module):
