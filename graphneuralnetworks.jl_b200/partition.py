@@ -200,19 +200,17 @@ def dist_gcn_conv(l, dg: DistGraph, x_local: torch.Tensor) -> torch.Tensor:
     The graph must have been partitioned with add_self_loops = l.add_self_loops.  Weight gradients are per-rank
     partial sums: all-reduce them like any data-parallel layer."""
     assert dg.self_loops == bool(l.add_self_loops)
+    from .layers import _linear
     W = l.weight
     Dout, Din = W.shape
-    xr = rows(x_local)
+    x = x_local
     if Dout < Din:
-        xr = xr @ W.t()
-    pr = _DistGCNPropagateFn.apply(xr, dg)
+        x = _linear(l, W, x, False)
+    pr = unrows(_DistGCNPropagateFn.apply(rows(x), dg))
     if Dout >= Din:
-        pr = pr @ W.t()
-    b = getattr(l, "bias", None)
-    if b is not None and b is not False:
-        pr = pr + b
-    sig = getattr(l, "σ", None) or getattr(l, "sigma", None) or (lambda v: v)
-    return unrows(sig(pr))
+        return _linear(l, W, pr, True)            # σ.(W * x .+ b): GEMM with the bias/relu epilogue
+    from .layers import _add_bias, _bias, _sigma
+    return _sigma(l)(_add_bias(pr, _bias(l)))
 
 
 # ---------------------------------------------------------------------------------------------------------
