@@ -99,8 +99,6 @@ _SIGS = {
     "gnnb_rmat_edges": (_int, [_i64, _i64, C.c_uint64, _vp, _vp, _vp]),
     "gnnb_set_chunk_edges": (_int, [_int]),
     "gnnb_set_kernel_variant": (_int, [_int]),
-    "gnnb_set_l2_hot_mb": (_int, [_int]),
-    "gnnb_set_w128_config": (_int, [_int]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

@@ -16,8 +16,6 @@ void set_error(const char* fmt, ...) {
 }
 
 extern int g_variant;   // segreduce.cu
-extern int g_l2_hot_mb;
-extern int g_w128_cfg;
 int edge_dot(gnnb_graph* g, const float* dout, const float* x, const float* cs, const float* ct, int64_t D,
              float* dw_coo, cudaStream_t st);
 int maxmin_bwd(gnnb_graph* g, const float* w_plan_src, const float* x, const float* dout, const float* out_fwd,
@@ -95,18 +93,8 @@ int gnnb_device_count(void) {
     return n;
 }
 int64_t gnnb_launch_count(void) { return g_launches.load(); }
-int gnnb_set_l2_hot_mb(int mb) {
-    if (mb < 0 || mb > 126) GNNB_FAIL(GNNB_EINVAL, "l2 hot budget must be in [0,126] MB");
-    gnnb::g_l2_hot_mb = mb;
-    return GNNB_OK;
-}
-int gnnb_set_w128_config(int c) {
-    if (c < 0 || c > 2) GNNB_FAIL(GNNB_EINVAL, "w128 config must be 0, 1 or 2");
-    gnnb::g_w128_cfg = c;
-    return GNNB_OK;
-}
 int gnnb_set_kernel_variant(int v) {
-    if (v < 0 || v > 6) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,6]");
+    if (v < 0 || v > 5) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,5]");
     gnnb::g_variant = v;
     return GNNB_OK;
 }

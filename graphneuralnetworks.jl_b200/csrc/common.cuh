@@ -51,8 +51,6 @@ struct Csr {
     int32_t* col = nullptr;     // [E] gathered node of each sorted edge
     int32_t* row = nullptr;     // [E] reduction row of each sorted edge (sorted, non-decreasing)
     int32_t* eid = nullptr;     // [E] COO position of each sorted edge (stable)
-    int32_t* colh = nullptr;    // [E] col | (popularity class << 30): class 3/2/1 = gathered node is among the
-                                //     32 K / 128 K / 512 K most often gathered ones (L2 eviction hints); may be null
     int32_t* long_rows = nullptr;  // rows with more than `chunk` edges (unordered)
     int32_t n_long = 0;
     int32_t nrows = 0;  // reduction rows (targets; sources when transposed)
@@ -99,7 +97,6 @@ struct SegArgs {
     int aggr = GNNB_SUM;
 };
 int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st);
-int build_popularity_classes(Csr& c, int64_t E, cudaStream_t st);
 // permute K floats per edge COO order -> plan order of `c`
 int permute_edge_values(const Csr& c, int64_t E, const float* coo_vals, int64_t K, float* plan_vals,
                         cudaStream_t st);

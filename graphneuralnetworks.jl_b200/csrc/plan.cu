@@ -89,58 +89,11 @@ __global__ void selfloop_rows_kernel(const int32_t* __restrict__ rowptr, int32_t
     }
 }
 
-__global__ void popularity_kernel(const int32_t* __restrict__ col, int64_t E, int32_t* __restrict__ pop) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < E) atomicAdd(pop + col[e], 1);       // integer counts: exact and order independent
-}
-__global__ void classify_kernel(const int32_t* __restrict__ col, int64_t E, const int32_t* __restrict__ pop,
-                                int32_t t1, int32_t t2, int32_t t3, int32_t* __restrict__ colh) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    const int32_t c = col[e];
-    const int32_t d = pop[c];
-    const uint32_t cls = (d >= t1) + (d >= t2) + (d >= t3);
-    colh[e] = (int32_t)((uint32_t)c | (cls << 30));
-}
-
 // ---- helpers ------------------------------------------------------------------------------------
 static void free_csr(Csr& c) {
-    cudaFree(c.rowptr); cudaFree(c.col); cudaFree(c.row); cudaFree(c.eid); cudaFree(c.colh);
+    cudaFree(c.rowptr); cudaFree(c.col); cudaFree(c.row); cudaFree(c.eid);
     cudaFree(c.long_rows); cudaFree(c.invdeg);
     c = Csr();
-}
-
-// Popularity classes of the gathered nodes (how often a node id occurs in `col`): rank thresholds at 32 K / 128 K /
-// 512 K nodes.  RMAT-like graphs concentrate most edges on few sources (config 2: the 128 K most popular rows are 62 %
-// of all gathers), so the fused kernel asks the L2 to keep those rows (evict_last) and to drop everything else first.
-int build_popularity_classes(Csr& c, int64_t E, cudaStream_t st) {
-    if (E == 0 || c.ncols <= 0 || c.ncols >= (1 << 30)) return GNNB_OK;   // two spare bits needed
-    int32_t *pop = nullptr, *sorted = nullptr;
-    void* tmp = nullptr;
-    GNNB_CUDA(cudaMalloc(&pop, sizeof(int32_t) * (size_t)c.ncols));
-    GNNB_CUDA(cudaMalloc(&sorted, sizeof(int32_t) * (size_t)c.ncols));
-    GNNB_CUDA(cudaMemsetAsync(pop, 0, sizeof(int32_t) * (size_t)c.ncols, st));
-    popularity_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(c.col, E, pop);
-    GNNB_LAUNCHED();
-    size_t tmp_bytes = 0;
-    GNNB_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, pop, sorted, c.ncols, 0, 32, st));
-    GNNB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
-    GNNB_CUDA(cub::DeviceRadixSort::SortKeysDescending(tmp, tmp_bytes, pop, sorted, c.ncols, 0, 32, st));
-    g_launches.fetch_add(4, std::memory_order_relaxed);
-    const int64_t ranks[3] = {512 * 1024, 128 * 1024, 32 * 1024};
-    int32_t thr[3];
-    for (int i = 0; i < 3; ++i) {
-        const int64_t r = ranks[i] < c.ncols ? ranks[i] : c.ncols;
-        GNNB_CUDA(cudaMemcpyAsync(&thr[i], sorted + (r - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    }
-    GNNB_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 3; ++i) if (thr[i] < 2) thr[i] = 2;             // a row gathered once cannot be re-used
-    if (!c.colh) GNNB_CUDA(cudaMalloc(&c.colh, sizeof(int32_t) * (size_t)E));
-    classify_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(c.col, E, pop, thr[0], thr[1], thr[2], c.colh);
-    GNNB_LAUNCHED();
-    GNNB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp); cudaFree(pop); cudaFree(sorted);
-    return GNNB_OK;
 }
 
 static int alloc_csr(Csr& c, int64_t E, int32_t nrows, int32_t ncols, int32_t chunk) {
@@ -204,7 +157,6 @@ int ensure_csr(gnnb_graph* g, bool transposed, cudaStream_t st) {
     rowptr_kernel<<<(unsigned)ceil_div(E + 1, 256), 256, 0, st>>>(c.row, E, nrows, c.rowptr);
     GNNB_LAUNCHED();
     GNNB_TRY(find_long_rows(c, g->chunk, st));
-    GNNB_TRY(build_popularity_classes(c, E, st));
     c.built = true;
     return GNNB_OK;
 }
@@ -354,7 +306,6 @@ static int derive_self_loop_csr(const Csr& o, Csr& c, int64_t E, int32_t n, int3
                                                                               c.row, c.col, c.eid);
     GNNB_LAUNCHED();
     GNNB_TRY(find_long_rows(c, chunk, st));
-    GNNB_TRY(build_popularity_classes(c, E + n, st));
     c.built = true;
     return GNNB_OK;
 }

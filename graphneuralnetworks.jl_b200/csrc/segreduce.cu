@@ -49,9 +49,8 @@ struct SegParams {
     float sign;     // +1, or -1 to turn MAX into MIN (min(m) = -max(-m))
 };
 
-// kernel variant: 0 = default (lean wide-row kernel with L2 hints for 64 < D <= 128, generic register-staged kernel
-// otherwise); 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu); 5 = generic kernel without the 64-register cap;
-// 6 = generic kernel (64-register cap) for every shape
+// kernel variant: 0 = register-staged kernel (default); 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu);
+// 5 = register-staged kernel without the 64-register cap
 int g_variant = 0;
 
 template <int VEC> struct VecT;
@@ -260,166 +259,6 @@ __global__ void fill_empty_rows_kernel(const int32_t* __restrict__ rowptr, float
     if (rowptr[r] == rowptr[r + 1]) out[i] = v;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// The hot shape: fp32 rows of 64 < D <= 128 floats (one warp = one row per LDG.128), i.e. BASELINE configs 2 and 4.
-// Same decomposition, same order of additions (bit-identical results) as seg_reduce_kernel, with the per-edge
-// instruction stream cut from ~64 to ~16 (ncu: the generic kernel ran at 68 % issue utilisation):
-//   * row starts come from ONE ballot per 32-edge batch instead of a shuffle + compare per edge;
-//   * the two scales are pre-multiplied per edge when the indices are loaded (exact when one of them is absent);
-//   * no per-slice offset arrays, 32-bit lane offsets, unpredicated loads in full batches;
-// and with L2 eviction hints driven by the plan's popularity classes (Csr::colh): rows of the most often gathered
-// nodes are loaded evict_last, everything else (cold rows, index streams) evict_first, the output is stored
-// evict_first.  On RMAT the 128 K most popular rows carry 62 % of all gathers and fit in the 126 MB L2.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg_hint(const float* p, uint64_t pol) {
-    float4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ int ldg_hint_i32(const int32_t* p, uint64_t pol) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ldg_hint_f32(const float* p, uint64_t pol) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void stg_hint(float* p, float4 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-}
-
-struct HotParams {
-    const int32_t* __restrict__ colh;   // col | class << 30
-    int32_t hotmin;                     // classes >= hotmin are kept in L2 (4 = none)
-};
-
-template <bool ISMAX, bool SCALE, bool HALO, int U, int MINB>
-__global__ void __launch_bounds__(256, MINB) seg_reduce_w128_kernel(const SegParams p, const HotParams hp) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const ChunkBounds cb = chunk_bounds(p.rowptr, p.row, k, p.chunk, p.E, p.nchunks);
-    if (cb.e_begin >= cb.e_end) return;                    // warp-uniform
-    const float neutral = ISMAX ? -CUDART_INF_F : 0.f;
-    const int D = (int)p.D;
-    const int loff = lane * 4;
-    const bool act = loff < D;                              // D may be < 128 (multiple of 4)
-    uint64_t pol_keep, pol_drop;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
-
-    float4 acc = make_float4(neutral, neutral, neutral, neutral);
-    int r = -1;
-    bool first_flush = true;
-    auto flush = [&](int rr, bool last) {
-        float* base;
-        bool raw;
-        if (first_flush && cb.head_partial) { base = p.ws + (size_t)(2 * k + 0) * D; raw = true; }
-        else if (last && cb.tail_partial) { base = p.ws + (size_t)(2 * k + 1) * D; raw = true; }
-        else { base = p.out + (size_t)rr * D; raw = false; }
-        first_flush = false;
-        if (act) {
-            const float4 v = raw ? acc : finish_row<float4>(acc, p, rr);
-            stg_hint(base + loff, v, pol_drop);
-        }
-    };
-    auto fill_gap = [&](int lo, int hi) {
-        if (!p.fill) return;
-        const float fv = ISMAX ? (p.sign < 0.f ? CUDART_INF_F : -CUDART_INF_F) : 0.f;
-        for (int q = lo + 1; q < hi; ++q)
-            if (act) stg_hint(p.out + (size_t)q * D + loff, make_float4(fv, fv, fv, fv), pol_drop);
-    };
-
-    int d_prev = -2;
-    for (int e = cb.e_begin; e < cb.e_end; e += 32) {       // warp-uniform bounds
-        const int my_e = e + lane;
-        const int nb = min(32, cb.e_end - e);
-        int c_l = 0, d_l = -1;
-        float s_l = 1.f;
-        if (lane < nb) {
-            c_l = ldg_hint_i32(hp.colh + my_e, pol_drop);
-            d_l = ldg_hint_i32(p.row + my_e, pol_drop);
-            if (SCALE) {
-                if (p.cs) s_l = __ldg(p.cs + (c_l & 0x3fffffff));
-                if (p.w) s_l = __fmul_rn(s_l, ldg_hint_f32(p.w + my_e, pol_drop));
-                if (ISMAX && p.sign < 0.f) s_l = -s_l;
-            }
-        }
-        int d_up = __shfl_up_sync(FULL, d_l, 1);
-        if (lane == 0) d_up = d_prev;
-        const unsigned starts = __ballot_sync(FULL, (lane < nb) && (d_l != d_up));
-        d_prev = __shfl_sync(FULL, d_l, nb - 1);
-#pragma unroll 1
-        for (int j0 = 0; j0 < nb; j0 += U) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int cw = __shfl_sync(FULL, c_l, j0 + u);
-                const int cj = cw & 0x3fffffff;
-                const uint64_t pol = ((unsigned)cw >> 30) >= (unsigned)hp.hotmin ? pol_keep : pol_drop;
-                const float* xr = (HALO && cj >= p.split) ? p.x2 + (size_t)(cj - p.split) * D : p.x + (size_t)cj * D;
-                v[u] = (act && (j0 + u) < nb) ? ldg_hint(xr + loff, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = j0 + u;
-                if (j < nb) {                               // warp-uniform
-                    if ((starts >> j) & 1u) {
-                        const int dj = __shfl_sync(FULL, d_l, j);
-                        if (r >= 0) { flush(r, false); fill_gap(r, dj); }
-                        else if (!cb.head_partial) fill_gap(cb.prev_row, dj);
-                        r = dj;
-                        acc = make_float4(neutral, neutral, neutral, neutral);
-                    }
-                    if (SCALE) {
-                        const float sj = __shfl_sync(FULL, s_l, j);
-                        acc = comb<ISMAX>(acc, v[u], sj, 1.f);
-                    } else {
-                        acc = ISMAX ? make_float4(fmaxf(acc.x, v[u].x), fmaxf(acc.y, v[u].y), fmaxf(acc.z, v[u].z), fmaxf(acc.w, v[u].w))
-                                    : make_float4(__fadd_rn(acc.x, v[u].x), __fadd_rn(acc.y, v[u].y), __fadd_rn(acc.z, v[u].z), __fadd_rn(acc.w, v[u].w));
-                    }
-                }
-            }
-        }
-    }
-    flush(r, true);
-    if (cb.e_end == p.E) fill_gap(r, p.nrows);
-}
-
-int g_l2_hot_mb = 72;   // bytes of popular rows asked to stay in L2 (gnnb_set_l2_hot_mb)
-int g_w128_cfg = 0;     // (loads in flight, CTAs/SM) point of the lean kernel: 0 = 8x4, 1 = 4x6, 2 = 8x3
-
-template <bool ISMAX>
-static int launch_w128(const SegParams& p, const Csr& c, cudaStream_t st) {
-    HotParams hp;
-    hp.colh = c.colh;
-    // largest class set whose rows fit the budget: class >= 1 : 512 K nodes, >= 2 : 128 K, >= 3 : 32 K
-    const double row_mb = (double)p.D * 4.0 / (1024.0 * 1024.0);
-    hp.hotmin = 4;
-    if (g_l2_hot_mb > 0) {
-        if (512.0 * 1024 * row_mb <= g_l2_hot_mb) hp.hotmin = 1;
-        else if (128.0 * 1024 * row_mb <= g_l2_hot_mb) hp.hotmin = 2;
-        else if (32.0 * 1024 * row_mb <= g_l2_hot_mb) hp.hotmin = 3;
-    }
-    const unsigned grid = (unsigned)ceil_div(p.nchunks, 8);
-    const bool scale = p.cs != nullptr || p.w != nullptr || p.sign < 0.f;
-    const bool halo = p.x2 != nullptr;
-#define W128(S, H)                                                                           \
-    do {                                                                                     \
-        if (g_w128_cfg == 1) seg_reduce_w128_kernel<ISMAX, S, H, 4, 6><<<grid, 256, 0, st>>>(p, hp);      \
-        else if (g_w128_cfg == 2) seg_reduce_w128_kernel<ISMAX, S, H, 8, 3><<<grid, 256, 0, st>>>(p, hp); \
-        else seg_reduce_w128_kernel<ISMAX, S, H, 8, 4><<<grid, 256, 0, st>>>(p, hp);                      \
-    } while (0)
-    if (scale) { if (halo) W128(true, true); else W128(true, false); }
-    else { if (halo) W128(false, true); else W128(false, false); }
-#undef W128
-    GNNB_LAUNCHED();
-    return GNNB_OK;
-}
-
 template <int VEC, int TPR, int K, bool ISMAX>
 static int launch_seg(const SegParams& p, cudaStream_t st) {
     const int gpb = 256 / TPR;  // groups per block
@@ -427,7 +266,7 @@ static int launch_seg(const SegParams& p, cudaStream_t st) {
     // One warp per 512 B row (D = 128 fp32): throughput follows the number of resident warps, not the loads per warp
     // (profiles/r1_seg_variants.md): cap the kernel at 64 registers => 4 CTAs x 8 warps per SM.  Variant 5 keeps the
     // uncapped build (77 registers, 24 warps) for A/B runs.
-    if (VEC == 4 && TPR == 32 && K == 1 && g_variant != 5) {   // variant 6 lands here as well
+    if (VEC == 4 && TPR == 32 && K == 1 && g_variant != 5) {
         seg_reduce_kernel<4, 32, 1, ISMAX, 8, 4><<<grid, 256, 0, st>>>(p);
         GNNB_LAUNCHED();
         return GNNB_OK;
@@ -496,12 +335,8 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
         bulk_rc = seg_reduce_bulk(c, a, g->E, g->chunk, p.ws, p.fill, g_variant - 1, st);
         if (bulk_rc != GNNB_OK && bulk_rc != GNNB_EUNSUPPORTED) return bulk_rc;
     }
-    if (bulk_rc != GNNB_OK && vec4 && g_variant == 0 && c.colh != nullptr && a.D > 64 && a.D <= 128) {
-        bulk_rc = ismax ? launch_w128<true>(p, c, st) : launch_w128<false>(p, c, st);
-        if (bulk_rc != GNNB_OK) return bulk_rc;
-    }
     if (bulk_rc == GNNB_OK) {
-        // done by the lean wide-row kernel or a shared-memory-staged kernel (segbulk.cu)
+        // done by a shared-memory-staged kernel (segbulk.cu)
     } else if (vec4) {
         int64_t nv = a.D / 4;
         tpr = (int)(nv >= 32 ? 32 : pow2ceil(nv));

@@ -242,17 +242,11 @@ int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t
  * power of two in [32, 4096]); affects plans created afterwards. */
 int gnnb_set_chunk_edges(int chunk);
 /* A/B switch for the fused segmented reduce on fp32 rows of 128/256/512 floats (results are bit-identical):
- * 0 = default: lean wide-row kernel with L2 eviction hints for 64 < D <= 128, generic register-staged LDG.128 kernel
- *     (capped at 64 registers, 32 resident warps/SM) otherwise;
+ * 0 = register-staged LDG.128 kernel, capped at 64 registers for 32 resident warps/SM (default, fastest measured);
  * 1 = TMA-staged: one cp.async.bulk (UBLKCP) per row into a shared-memory ring, mbarrier completion;
- * 2..4 = cp.async (LDGSTS) rings of 64/32/16 rows per warp;  5 = generic kernel without the register cap;
- * 6 = generic kernel for every shape.
+ * 2..4 = cp.async (LDGSTS) rings of 64/32/16 rows per warp;  5 = register-staged kernel without the register cap.
  * Measurements: profiles/r1_seg_variants.md. */
 int gnnb_set_kernel_variant(int v);
-/* MB of the most often gathered feature rows the fused kernel asks the L2 to keep (evict_last), 0 = no hints;
- * default 72.  And the (loads in flight x resident CTAs) point of the wide-row kernel: 0 = 8x4, 1 = 4x6, 2 = 8x3. */
-int gnnb_set_l2_hot_mb(int mb);
-int gnnb_set_w128_config(int c);
 
 #ifdef __cplusplus
 }

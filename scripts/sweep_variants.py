@@ -16,9 +16,7 @@ x = torch.randn(n, D, device=dev)
 out = torch.empty_like(x)
 res = []
 CHUNKS = [int(c) for c in os.environ.get('CHUNKS', '128').split(',')]
-VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '0,6').split(',')]
-HOT = [int(v) for v in os.environ.get('HOT', '72').split(',')]
-CFGS = [int(v) for v in os.environ.get('CFGS', '0').split(',')]
+VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '0,5,6,7,8').split(',')]
 for chunk in CHUNKS:
     gnn._lib.check(lib.gnnb_set_chunk_edges(chunk))
     g = gnn.rmat_graph(n, E, 17, device=dev)
@@ -26,11 +24,9 @@ for chunk in CHUNKS:
     gnn._lib.check(lib.gnnb_graph_csr(g2.plan().h, 1, None, None, None, None))
     c = gnn.layers._gcn_c(g2)
     ref = None
-    for v, hot, cfg in [(v, h, c) for v in VARIANTS for h in (HOT if v == 0 else [0]) for c in (CFGS if v == 0 else [0])]:
+    for v in VARIANTS:
         gnn._lib.check(lib.gnnb_set_kernel_variant(v))
-        gnn._lib.check(lib.gnnb_set_l2_hot_mb(hot))
-        gnn._lib.check(lib.gnnb_set_w128_config(cfg))
-        row = {"chunk": chunk, "variant": v, "hot_mb": hot, "cfg": cfg}
+        row = {"chunk": chunk, "variant": v}
         for tr in (0, 1):
             for _ in range(2):
                 gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, c.data_ptr(), D, out.data_ptr(), None))
@@ -52,6 +48,4 @@ for chunk in CHUNKS:
     del g, g2, c
     torch.cuda.empty_cache()
 gnn._lib.lib.gnnb_set_kernel_variant(0)
-gnn._lib.lib.gnnb_set_l2_hot_mb(72)
-gnn._lib.lib.gnnb_set_w128_config(0)
 gnn._lib.lib.gnnb_set_chunk_edges(128)
