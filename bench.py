@@ -279,8 +279,12 @@ def run_ours(args):
     kms = 0.5 * (kt[0] + kt[1])
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (kms * 1e-3) / 1e9
+    # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/r1_seg_r1b_ncu_raw.csv:
+    # dram__bytes_read.sum 36.83 GB + dram__bytes_write.sum 6.02 GB); only valid for the default workload
+    traffic = 42.85e9 if (n, E, D) == (N_NODES, N_EDGES, DIM) else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "gnnb::seg_reduce_kernel<4,32,1,false> (fused GCN propagate, D=128)",
+            "traffic": traffic, "traffic_GBps": (traffic / (kms * 1e-3) / 1e9) if traffic else None,
+            "kernel": "gnnb::seg_reduce_kernel<4,32,1,false,8,4> (fused GCN propagate, D=128)",
             "kernel_ms": {"forward": kt[0], "transposed": kt[1]}, "algorithmic_bytes_per_launch": alg_bytes,
             "compulsory_bytes_per_launch": compulsory, "peak_source": peak_src,
             "share_of_step": 2 * kms / ms}
