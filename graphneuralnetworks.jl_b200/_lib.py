@@ -91,6 +91,8 @@ _SIGS = {
     "gnnb_linear": (_int, [_f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _f32p, _vp]),
     "gnnb_linear_bwd": (_int, [_f32p, _f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _vp]),
     "gnnb_dense_set_emulation": (_int, [_int]),
+    "gnnb_dense_set_tensor_core_kernel": (_int, [_int]),
+    "gnnb_dense_tc_error": (_int, []),
     "gnnb_dense_emulation_active": (_int, []),
     "gnnb_gather_rows": (_int, [_vp, _i64, _f32p, _i64, _f32p, _vp]),
     "gnnb_propagate_halo": (_int, [_vp, _int, _int, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64, _f32p, _vp]),

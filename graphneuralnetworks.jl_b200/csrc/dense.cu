@@ -110,6 +110,16 @@ static int matmul(cublasOperation_t ta, cublasOperation_t tb, int64_t m, int64_t
 }
 }  // namespace lt
 
+int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, int64_t M, int64_t K, int64_t Nout, float* y,
+                  cudaStream_t st);   // dense_tc.cu
+int linear_tf32x3_error();
+extern int g_tc_enabled;
+
+__global__ void transpose_small_kernel(const float* __restrict__ w, int rows, int cols, float* __restrict__ wt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) { const int r = i / cols, c = i % cols; wt[(size_t)c * rows + r] = w[i]; }
+}
+
 // dpre = dy * (y > 0) (relu pullback, y = forward output) or dpre = dy; partial column sums per block for db
 template <int RELU>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
@@ -161,6 +171,8 @@ using namespace gnnb;
 
 extern "C" {
 
+int gnnb_dense_set_tensor_core_kernel(int on) { g_tc_enabled = on ? 1 : 0; return GNNB_OK; }
+int gnnb_dense_tc_error(void) { return linear_tf32x3_error(); }
 int gnnb_dense_set_emulation(int on) { lt::want_emulation = on ? 1 : 0; if (on && lt::emulation == 0) lt::emulation = -1; return GNNB_OK; }
 int gnnb_dense_emulation_active(void) { return lt::emulation; }
 
@@ -169,6 +181,10 @@ int gnnb_linear(const float* x, const float* W, const float* bias, int relu, int
     if (N < 0 || Din <= 0 || Dout <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
     if (N == 0) return GNNB_OK;
     if (!x || !W || !y) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
+    {   // hand-written tcgen05 3xTF32 kernel for K, Nout <= 128 (dense_tc.cu); cuBLASLt for every other shape
+        const int rc = linear_tf32x3(x, W, bias, relu, N, Din, Dout, y, (cudaStream_t)stream);
+        if (rc != GNNB_EUNSUPPORTED) return rc;
+    }
     // column-major: Y(Dout x N) = W(Dout x Din) X(Din x N); W is stored (Dout, Din) row-major = col-major (Din x Dout)
     return lt::matmul(CUBLAS_OP_T, CUBLAS_OP_N, Dout, N, Din, W, Din, x, Din, y, Dout, bias, relu, (cudaStream_t)stream);
 }
@@ -206,6 +222,16 @@ int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float
         if (relu) dpre = dpre_ws;
     } else if (db && N == 0) {
         GNNB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Dout, st));
+    }
+    // dX = dPre * W : rows of dPre (K = Dout) against W^T stored K-major => the same tcgen05 kernel on a transposed copy of W
+    if (dx && g_tc_enabled && Dout % 32 == 0 && Dout <= 128 && Din % 16 == 0 && Din <= 128 && Din >= 16) {
+        static float* wt = nullptr;
+        if (!wt) GNNB_CUDA(cudaMalloc(&wt, sizeof(float) * 128 * 128));
+        transpose_small_kernel<<<(unsigned)ceil_div(Dout * Din, 256), 256, 0, st>>>(W, (int)Dout, (int)Din, wt);
+        GNNB_LAUNCHED();
+        const int rc = linear_tf32x3(dpre, wt, nullptr, 0, N, Dout, Din, dx, st);
+        if (rc == GNNB_OK) dx = nullptr;
+        else if (rc != GNNB_EUNSUPPORTED) return rc;
     }
     // dX(Din x N) = W^T-as-stored(Din x Dout) dPre(Dout x N)
     if (dx) GNNB_TRY(lt::matmul(CUBLAS_OP_N, CUBLAS_OP_N, Din, N, Dout, W, Din, dpre, Dout, dx, Din, nullptr, 0, st));

@@ -1,0 +1,280 @@
+// dense_tc.cu — hand-written tcgen05 kernel for the per-layer dense contraction  Y = act(X * W^T + b)
+// (GNNlib/src/layers/conv.jl:69-71 `l.σ.(weight * x .+ l.bias)`; X is (N rows, K), W is (Nout, K) row-major).
+//
+// fp32 in, fp32 out, fp32-level accuracy on the TF32 tensor cores by the 3xTF32 split:
+//     x = x_big + x_small,  x_big = x with the low 13 mantissa bits cleared (what kind::tf32 reads anyway),
+//     x_small = x - x_big (exact in fp32);   x*w ~= x_big*w_big + x_big*w_small + x_small*w_big
+// (the dropped x_small*w_small term is 2^-22 relative).  Accumulation is fp32 in TMEM.
+//
+// Shape: one persistent CTA per SM.  W (<= 128 x 128) is split once into two K-major 128B-swizzled shared-memory
+// images (w_big, w_small).  Row tiles of 128 rows of X stream through a 2-stage ring, one 32-float K-block per stage:
+//   warps 0-7   loaders : coalesced LDG.128 of the K-block, split in registers, st.shared into the canonical UMMA
+//                         K-major SWIZZLE_128B layout (x_big, x_small), fence.proxy.async, arrive on full[stage]
+//   warp  8     MMA     : one elected thread issues 12 tcgen05.mma.kind::tf32 (M=128, N=Nout, K=8) per K-block into a
+//                         double-buffered TMEM accumulator; tcgen05.commit frees the stage / publishes the tile
+//   warps 9-12  epilogue: tcgen05.ld 32 lanes x 32 columns, + bias, relu, 16 B stores of the finished rows
+// The kernel is HBM-bound by design (2 x 4 x K bytes per row against 6 K^2 flops on 1.1 PF/s of TF32).
+// Every mbarrier wait is bounded: a broken pipeline makes the kernel flag an error and drain instead of hanging.
+#include "common.cuh"
+
+namespace gnnb {
+
+namespace tc {
+constexpr int BM = 128;           // rows per tile (UMMA M)
+constexpr int BK = 32;            // floats per K-block = one 128 B swizzle row
+constexpr int NSTAGE = 2;
+constexpr int LOADERS = 256;      // warps 0-7
+constexpr int MMA_WARP = 8;
+constexpr int EPI_WARP0 = 9;      // warps 9-12
+constexpr int THREADS = 13 * 32;
+constexpr int KBLK_BYTES = BM * 128;          // one operand image of a K-block: 128 rows x 128 B = 16 KB
+constexpr int W_BYTES = 4 * KBLK_BYTES;       // up to K = 128: 64 KB per image
+constexpr int SMEM_W_BIG = 0;
+constexpr int SMEM_W_SMALL = W_BYTES;
+constexpr int SMEM_A = 2 * W_BYTES;           // stages: [big 16 KB][small 16 KB]
+constexpr int SMEM_BIAS = SMEM_A + NSTAGE * 2 * KBLK_BYTES;
+constexpr int SMEM_BAR = SMEM_BIAS + 512;
+constexpr int SMEM_TOTAL = SMEM_BAR + 128;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool bar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: returns false (and raises *err) if the barrier never flips
+__device__ __forceinline__ bool bar_wait(uint32_t bar, uint32_t parity, int* err) {
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        if (bar_try(bar, parity)) return true;
+        if ((spin & 1023) == 1023 && *(volatile int*)err) return false;
+    }
+    atomicExch(err, 1);
+    return false;
+}
+__device__ __forceinline__ float tf32_big(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+struct Params {
+    const float* __restrict__ x;     // [M][K]
+    const float* __restrict__ w;     // [Nout][K]
+    const float* __restrict__ bias;  // [Nout] or null
+    float* __restrict__ y;           // [M][Nout]
+    int64_t M;
+    int K, Nout, relu;
+    int* err;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KB = p.K / BK;                                   // K-blocks per tile (<= 4)
+    const int64_t ntiles = (p.M + BM - 1) / BM;
+    const uint32_t sbase = s_u32(smem);
+    const uint32_t bar_full = sbase + SMEM_BAR;                // [NSTAGE]
+    const uint32_t bar_empty = bar_full + 8 * NSTAGE;          // [NSTAGE]
+    const uint32_t bar_tfull = bar_empty + 8 * NSTAGE;         // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * (2 * NSTAGE + 4));
+    float* sbias = reinterpret_cast<float*>(smem + SMEM_BIAS);
+
+    // ---- one-time setup: barriers, TMEM, bias, W split into the two swizzled K-major images
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { bar_init(bar_full + 8 * s, LOADERS); bar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8 * a, 1); bar_init(bar_tempty + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 128; i += THREADS) sbias[i] = (p.bias && i < p.Nout) ? p.bias[i] : 0.f;
+    {
+        const int kv = p.K >> 2;                               // float4 per row of W
+        for (int idx = tid; idx < p.Nout * kv; idx += THREADS) {
+            const int n = idx / kv, c4 = idx - n * kv, kb = c4 >> 3, c = c4 & 7;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.K) + c4);
+            const float4 b = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+            const float4 s = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+            const int off = kb * KBLK_BYTES + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4);
+            *reinterpret_cast<float4*>(smem + SMEM_W_BIG + off) = b;
+            *reinterpret_cast<float4*>(smem + SMEM_W_SMALL + off) = s;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // W images are read by the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ================= loaders =================
+        const int c = tid & 7, r32 = tid >> 3, rr = r32 & 7;
+        uint32_t it = 0;
+        bool alive = true;
+        for (int64_t tile = blockIdx.x; alive && tile < ntiles; tile += gridDim.x) {
+            const int64_t m0 = tile * BM;
+            for (int kb = 0; alive && kb < KB; ++kb, ++it) {
+                const int stage = it % NSTAGE;
+                float4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t row = m0 + r32 + 32 * i;
+                    v[i] = (row < p.M) ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.K + kb * BK) + c)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (!bar_wait(bar_empty + 8 * stage, ((it / NSTAGE) & 1) ^ 1, p.err)) { alive = false; break; }
+                unsigned char* abig = smem + SMEM_A + stage * 2 * KBLK_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b = make_float4(tf32_big(v[i].x), tf32_big(v[i].y), tf32_big(v[i].z), tf32_big(v[i].w));
+                    const float4 s = make_float4(v[i].x - b.x, v[i].y - b.y, v[i].z - b.z, v[i].w - b.w);
+                    const int off = ((r32 >> 3) + 4 * i) * 1024 + rr * 128 + ((c ^ rr) << 4);
+                    *reinterpret_cast<float4*>(abig + off) = b;
+                    *reinterpret_cast<float4*>(abig + KBLK_BYTES + off) = s;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bar_arrive(bar_full + 8 * stage);
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nout >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        uint32_t it = 0, tcount = 0;
+        bool alive = true;
+        for (int64_t tile = blockIdx.x; alive && tile < ntiles; tile += gridDim.x, ++tcount) {
+            const int acc = tcount & 1;
+            if (!bar_wait(bar_tempty + 8 * acc, ((tcount >> 1) & 1) ^ 1, p.err)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + acc * 128;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int stage = it % NSTAGE;
+                if (!bar_wait(bar_full + 8 * stage, (it / NSTAGE) & 1, p.err)) { alive = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t a_big = sbase + SMEM_A + stage * 2 * KBLK_BYTES, a_small = a_big + KBLK_BYTES;
+                    const uint32_t w_big = sbase + SMEM_W_BIG + kb * KBLK_BYTES, w_small = sbase + SMEM_W_SMALL + kb * KBLK_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {              // 4 x (K = 8 tf32 = 32 B) per K-block, small terms first
+                        const uint32_t o = j * 32;
+                        umma_tf32(tmem_d, umma_desc(a_small + o), umma_desc(w_big + o), idesc, (kb | j) != 0);
+                        umma_tf32(tmem_d, umma_desc(a_big + o), umma_desc(w_small + o), idesc, 1u);
+                        umma_tf32(tmem_d, umma_desc(a_big + o), umma_desc(w_big + o), idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8 * stage);        // smem stage reusable once these MMAs have read it
+                    if (kb == KB - 1) umma_commit(bar_tfull + 8 * acc);   // accumulator complete
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue (4 warps; warp w owns TMEM lanes 32*(w%4) .. +31 = rows of the tile) =================
+        const int q = warp & 3;
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+            const int acc = tcount & 1;
+            if (!bar_wait(bar_tfull + 8 * acc, (tcount >> 1) & 1, p.err)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t row = tile * BM + q * 32 + lane;
+            float* yrow = p.y + (size_t)row * p.Nout;
+            for (int c0 = 0; c0 < p.Nout; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (c0 + j < p.Nout) {
+                            float4 o;
+                            o.x = __uint_as_float(r[j]) + sbias[c0 + j];
+                            o.y = __uint_as_float(r[j + 1]) + sbias[c0 + j + 1];
+                            o.z = __uint_as_float(r[j + 2]) + sbias[c0 + j + 2];
+                            o.w = __uint_as_float(r[j + 3]) + sbias[c0 + j + 3];
+                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            *reinterpret_cast<float4*>(yrow + c0 + j) = o;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+    // ---- teardown
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+}  // namespace tc
+
+static int* g_tc_err = nullptr;
+int g_tc_enabled = 1;
+
+// returns GNNB_EUNSUPPORTED (no error text) when the shape is not covered by the tensor-core kernel
+int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, int64_t M, int64_t K, int64_t Nout, float* y,
+                  cudaStream_t st) {
+    if (!g_tc_enabled) return GNNB_EUNSUPPORTED;
+    if (K % 32 != 0 || K > 128 || Nout % 16 != 0 || Nout > 128 || Nout < 16) return GNNB_EUNSUPPORTED;
+    if (((uintptr_t)x & 15) || ((uintptr_t)W & 15) || ((uintptr_t)y & 15)) return GNNB_EUNSUPPORTED;
+    if (M == 0) return GNNB_OK;
+    static bool configured = false;
+    static int nsm = 0;
+    if (!configured) {
+        GNNB_CUDA(cudaFuncSetAttribute(tc::linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+        int dev = 0;
+        GNNB_CUDA(cudaGetDevice(&dev));
+        GNNB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        GNNB_CUDA(cudaMalloc(&g_tc_err, sizeof(int)));
+        GNNB_CUDA(cudaMemset(g_tc_err, 0, sizeof(int)));
+        configured = true;
+    }
+    tc::Params p;
+    p.x = x; p.w = W; p.bias = bias; p.y = y; p.M = M; p.K = (int)K; p.Nout = (int)Nout; p.relu = relu; p.err = g_tc_err;
+    const int64_t ntiles = ceil_div(M, tc::BM);
+    const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
+    tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(p);
+    GNNB_LAUNCHED();
+    return GNNB_OK;
+}
+
+// pipeline watchdog: non-zero if a bounded mbarrier wait expired in any launch so far (then results are invalid)
+int linear_tf32x3_error() {
+    if (!g_tc_err) return 0;
+    int e = 0;
+    cudaMemcpy(&e, g_tc_err, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}
+
+}  // namespace gnnb

@@ -201,6 +201,11 @@ int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float
 /* 1 (default) = try the fp32-emulated tensor-core GEMM; 0 = force the SIMT sgemm.  *_active: -1 not yet used,
  * 0 unavailable / off, 1 in use. */
 int gnnb_dense_set_emulation(int on);
+/* The hand-written tcgen05 kernel (csrc/dense_tc.cu: 3xTF32 split, TMEM accumulators, bias/relu epilogue) serves
+ * Din, Dout <= 128 (Din % 32 == 0, Dout % 16 == 0) for gnnb_linear and the dx part of gnnb_linear_bwd; 0 switches it
+ * off (cuBLASLt everywhere).  gnnb_dense_tc_error() != 0 means one of its bounded pipeline waits expired. */
+int gnnb_dense_set_tensor_core_kernel(int on);
+int gnnb_dense_tc_error(void);
 int gnnb_dense_emulation_active(void);
 
 /* ------------------------------------------------- node-partitioned shards

@@ -650,14 +650,18 @@ def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
 
 
 # --------------------------------------------------------------------------------------------- dense layer part
-@pytest.mark.parametrize("N,Din,Dout", [(1000, 128, 128), (777, 16, 8), (5000, 64, 256), (33, 1432, 16), (0, 8, 8)])
+@pytest.mark.parametrize("N,Din,Dout", [(1000, 128, 128), (777, 16, 8), (5000, 64, 256), (33, 1432, 16), (0, 8, 8),
+                                        (4096, 64, 128), (130000, 128, 64), (300, 32, 16), (129, 96, 48), (1, 128, 128)])
 @pytest.mark.parametrize("relu_flag,with_bias", [(1, True), (0, True), (1, False), (0, False)])
 @pytest.mark.parametrize("emulate", [1, 0])
 def test_linear_c_abi(gnn, N, Din, Dout, relu_flag, with_bias, emulate):
+    # emulate=1: hand-written tcgen05 3xTF32 kernel where the shape allows, cuBLASLt fp32-emulated GEMM elsewhere;
+    # emulate=0: cuBLASLt SIMT sgemm only (tensor-core kernel switched off)
     """gnnb_linear / gnnb_linear_bwd (σ.(W*x .+ b), conv.jl:69-71) against fp64: the fp32-emulated tensor-core GEMM must
     stay inside the 1e-5 bar, like the SIMT sgemm."""
     lib = gnn._lib.lib
     lib.gnnb_dense_set_emulation(emulate)
+    lib.gnnb_dense_set_tensor_core_kernel(emulate)
     try:
         gen = torch.Generator(device="cuda").manual_seed(N + Din)
         x = torch.randn(N, Din, device="cuda", generator=gen)
@@ -681,9 +685,11 @@ def test_linear_c_abi(gnn, N, Din, Dout, relu_flag, with_bias, emulate):
             assert rel(db.cpu(), dpre.sum(0).cpu()) < 5e-6
         else:
             assert (db == 0).all()
-        assert lib.gnnb_dense_emulation_active() in (0, 1)
+        assert lib.gnnb_dense_emulation_active() in (-1, 0, 1)
+        assert lib.gnnb_dense_tc_error() == 0          # the tcgen05 pipeline never timed out
     finally:
         lib.gnnb_dense_set_emulation(1)
+        lib.gnnb_dense_set_tensor_core_kernel(1)
 
 
 # ---------------------------------------------------------------------------------- full-size properties (config 2)
