@@ -259,120 +259,6 @@ __global__ void fill_empty_rows_kernel(const int32_t* __restrict__ rowptr, float
     if (rowptr[r] == rowptr[r + 1]) out[i] = v;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Lean kernel for the hot shape: fp32 rows of 64 < D <= 128 floats (one warp = one row per LDG.128).  Same
-// decomposition and order of additions (bit-identical results) as seg_reduce_kernel with fewer instructions per edge:
-// row starts from ONE ballot per 32-edge batch instead of a shuffle + compare per edge, the two scales pre-multiplied
-// when the indices are loaded (exact when one of them is absent), no per-slice offset arrays, 32-bit lane offsets.
-// A/B against the generic kernel: gnnb_set_kernel_variant(7..9) selects it with (U loads, MINB CTAs) = 8x4, 4x6, 8x5.
-// ---------------------------------------------------------------------------------------------------------
-template <bool ISMAX, bool SCALE, bool HALO, int U, int MINB>
-__global__ void __launch_bounds__(256, MINB) seg_reduce_w128_kernel(const SegParams p) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const ChunkBounds cb = chunk_bounds(p.rowptr, p.row, k, p.chunk, p.E, p.nchunks);
-    if (cb.e_begin >= cb.e_end) return;                    // warp-uniform
-    const float neutral = ISMAX ? -CUDART_INF_F : 0.f;
-    const int D = (int)p.D;
-    const int loff = lane * 4;
-    const bool act = loff < D;                              // D may be < 128 (multiple of 4)
-
-    float4 acc = make_float4(neutral, neutral, neutral, neutral);
-    int r = -1;
-    bool first_flush = true;
-    auto flush = [&](int rr, bool last) {
-        float* base;
-        bool raw;
-        if (first_flush && cb.head_partial) { base = p.ws + (size_t)(2 * k + 0) * D; raw = true; }
-        else if (last && cb.tail_partial) { base = p.ws + (size_t)(2 * k + 1) * D; raw = true; }
-        else { base = p.out + (size_t)rr * D; raw = false; }
-        first_flush = false;
-        if (act) {
-            const float4 v = raw ? acc : finish_row<float4>(acc, p, rr);
-            *reinterpret_cast<float4*>(base + loff) = v;
-        }
-    };
-    auto fill_gap = [&](int lo, int hi) {
-        if (!p.fill) return;
-        const float fv = ISMAX ? (p.sign < 0.f ? CUDART_INF_F : -CUDART_INF_F) : 0.f;
-        for (int q = lo + 1; q < hi; ++q)
-            if (act) *reinterpret_cast<float4*>(p.out + (size_t)q * D + loff) = make_float4(fv, fv, fv, fv);
-    };
-
-    int d_prev = -2;
-    for (int e = cb.e_begin; e < cb.e_end; e += 32) {       // warp-uniform bounds
-        const int my_e = e + lane;
-        const int nb = min(32, cb.e_end - e);
-        int c_l = 0, d_l = -1;
-        float s_l = 1.f;
-        if (lane < nb) {
-            c_l = __ldg(p.col + my_e);
-            d_l = __ldg(p.row + my_e);
-            if (SCALE) {
-                if (p.cs) s_l = __ldg(p.cs + c_l);
-                if (p.w) s_l = __fmul_rn(s_l, __ldg(p.w + my_e));
-                if (ISMAX && p.sign < 0.f) s_l = -s_l;
-            }
-        }
-        int d_up = __shfl_up_sync(FULL, d_l, 1);
-        if (lane == 0) d_up = d_prev;
-        const unsigned starts = __ballot_sync(FULL, (lane < nb) && (d_l != d_up));
-        d_prev = __shfl_sync(FULL, d_l, nb - 1);
-#pragma unroll 1
-        for (int j0 = 0; j0 < nb; j0 += U) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int cj = __shfl_sync(FULL, c_l, j0 + u);
-                const float* xr = (HALO && cj >= p.split) ? p.x2 + (size_t)(cj - p.split) * D : p.x + (size_t)cj * D;
-                v[u] = (act && (j0 + u) < nb) ? __ldg(reinterpret_cast<const float4*>(xr + loff)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = j0 + u;
-                if (j < nb) {                               // warp-uniform
-                    if ((starts >> j) & 1u) {
-                        const int dj = __shfl_sync(FULL, d_l, j);
-                        if (r >= 0) { flush(r, false); fill_gap(r, dj); }
-                        else if (!cb.head_partial) fill_gap(cb.prev_row, dj);
-                        r = dj;
-                        acc = make_float4(neutral, neutral, neutral, neutral);
-                    }
-                    if (SCALE) {
-                        const float sj = __shfl_sync(FULL, s_l, j);
-                        acc = comb<ISMAX>(acc, v[u], sj, 1.f);
-                    } else {
-                        acc = ISMAX ? make_float4(fmaxf(acc.x, v[u].x), fmaxf(acc.y, v[u].y), fmaxf(acc.z, v[u].z), fmaxf(acc.w, v[u].w))
-                                    : make_float4(__fadd_rn(acc.x, v[u].x), __fadd_rn(acc.y, v[u].y), __fadd_rn(acc.z, v[u].z), __fadd_rn(acc.w, v[u].w));
-                    }
-                }
-            }
-        }
-    }
-    flush(r, true);
-    if (cb.e_end == p.E) fill_gap(r, p.nrows);
-}
-
-
-template <bool ISMAX>
-static int launch_w128(const SegParams& p, int cfg, cudaStream_t st) {
-    const unsigned grid = (unsigned)ceil_div(p.nchunks, 8);
-    const bool scale = p.cs != nullptr || p.w != nullptr || p.sign < 0.f;
-    const bool halo = p.x2 != nullptr;
-#define W128(S, H)                                                                           \
-    do {                                                                                     \
-        if (cfg == 1) seg_reduce_w128_kernel<ISMAX, S, H, 4, 6><<<grid, 256, 0, st>>>(p);      \
-        else if (cfg == 2) seg_reduce_w128_kernel<ISMAX, S, H, 8, 5><<<grid, 256, 0, st>>>(p); \
-        else seg_reduce_w128_kernel<ISMAX, S, H, 8, 4><<<grid, 256, 0, st>>>(p);               \
-    } while (0)
-    if (scale) { if (halo) W128(true, true); else W128(true, false); }
-    else { if (halo) W128(false, true); else W128(false, false); }
-#undef W128
-    GNNB_LAUNCHED();
-    return GNNB_OK;
-}
-
 template <int VEC, int TPR, int K, bool ISMAX>
 static int launch_seg(const SegParams& p, cudaStream_t st) {
     const int gpb = 256 / TPR;  // groups per block
@@ -449,12 +335,8 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
         bulk_rc = seg_reduce_bulk(c, a, g->E, g->chunk, p.ws, p.fill, g_variant - 1, st);
         if (bulk_rc != GNNB_OK && bulk_rc != GNNB_EUNSUPPORTED) return bulk_rc;
     }
-    if (bulk_rc != GNNB_OK && vec4 && g_variant >= 7 && g_variant <= 9 && a.D > 64 && a.D <= 128) {
-        bulk_rc = ismax ? launch_w128<true>(p, g_variant - 7, st) : launch_w128<false>(p, g_variant - 7, st);
-        if (bulk_rc != GNNB_OK) return bulk_rc;
-    }
     if (bulk_rc == GNNB_OK) {
-        // done by the lean kernel or a shared-memory-staged kernel (segbulk.cu)
+        // done by a shared-memory-staged kernel (segbulk.cu)
     } else if (vec4) {
         int64_t nv = a.D / 4;
         tpr = (int)(nv >= 32 ? 32 : pow2ceil(nv));

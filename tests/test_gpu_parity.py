@@ -584,7 +584,7 @@ def test_tma_staged_variant_is_bit_identical(graph, oracle, gnn, variant, D, agg
     base = gnn.propagate(gnn.copy_xj, g, aggr, xj=x)
     base_w = gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w)
     assert rel(np_rows(base), oracle.propagate_unfused(aggr, s, t, n, np_rows(x).astype(np.float64))) < TOL
-    for v in (1, 2, 3, 4, 5, 7, 8, 9):
+    for v in (1, 2, 3, 4, 5):
         variant(v)
         assert torch.equal(gnn.propagate(gnn.copy_xj, g, aggr, xj=x), base), f"variant {v}"
         assert torch.equal(gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w), base_w), f"variant {v} weighted"
@@ -604,7 +604,7 @@ def test_tma_staged_variant_large_chunks(gnn, oracle, variant):
             g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
             l = gnn.GCNConv(128, 128, device="cuda")
             outs = []
-            for v in (0, 1, 3, 5, 7, 8):
+            for v in (0, 1, 3, 5):
                 variant(v)
                 g2 = gnn.add_self_loops(g)
                 c = gnn.layers._gcn_c(g2)
@@ -634,7 +634,7 @@ def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
     ct = torch.rand(n, device="cuda") + 0.5
     ref = torch.empty_like(x)
     p = g.plan()
-    for v in (0, 1, 7):
+    for v in (0, 1, 5):
         variant(v)
         gnn._lib.check(lib.gnnb_propagate(p.h, 0, gnn._lib.COPY_XJ, gnn._lib.SUM, x.data_ptr(), None, cs.data_ptr(),
                                           ct.data_ptr(), D, ref.data_ptr(), None))
