@@ -113,6 +113,7 @@ static int matmul(cublasOperation_t ta, cublasOperation_t tb, int64_t m, int64_t
 int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, int64_t M, int64_t K, int64_t Nout, float* y,
                   cudaStream_t st);   // dense_tc.cu
 int linear_tf32x3_error();
+int dw_tf32x3(const float* dpre, const float* x, int64_t M, int64_t Din, int64_t Dout, float* dW, cudaStream_t st);
 extern int g_tc_enabled;
 
 __global__ void transpose_small_kernel(const float* __restrict__ w, int rows, int cols, float* __restrict__ wt) {
@@ -238,6 +239,9 @@ int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float
     // dW row-major (Dout, Din) = col-major (Din x Dout) = X(Din x N) dPre^T(N x Dout)
     if (dW) {
         if (!x) GNNB_FAIL(GNNB_EINVAL, "dW needs x");
+        const int rc = dw_tf32x3(dpre, x, N, Din, Dout, dW, st);      // tcgen05, MN-major operands, split-K
+        if (rc == GNNB_OK) return GNNB_OK;
+        if (rc != GNNB_EUNSUPPORTED) return rc;
         GNNB_TRY(lt::matmul(CUBLAS_OP_N, CUBLAS_OP_T, Din, Dout, N, x, Din, dpre, Dout, dW, Din, nullptr, 0, st));
     }
     return GNNB_OK;

@@ -22,7 +22,7 @@ namespace gnnb {
 namespace tc {
 constexpr int BM = 128;           // rows per tile (UMMA M)
 constexpr int BK = 32;            // floats per K-block = one 128 B swizzle row
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 3;
 constexpr int LOADERS = 256;      // warps 0-7
 constexpr int MMA_WARP = 8;
 constexpr int EPI_WARP0 = 9;      // warps 9-12
@@ -140,32 +140,40 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
     if (warp < 8) {
         // ================= loaders =================
         const int c = tid & 7, r32 = tid >> 3, rr = r32 & 7;
-        uint32_t it = 0;
-        bool alive = true;
-        for (int64_t tile = blockIdx.x; alive && tile < ntiles; tile += gridDim.x) {
-            const int64_t m0 = tile * BM;
-            for (int kb = 0; alive && kb < KB; ++kb, ++it) {
-                const int stage = it % NSTAGE;
-                float4 v[4];
+        // flattened (tile, K-block) sequence of this CTA; the next item is prefetched into registers while the current
+        // one waits for its shared-memory slot: 8 x 16 B per thread (32 KB per SM) in flight
+        const int64_t my_tiles = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t total = my_tiles * KB;
+        auto fetch = [&](int64_t item, float4* v) {
+            const int64_t tile = blockIdx.x + (item / KB) * gridDim.x;
+            const int kb = (int)(item % KB);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t row = m0 + r32 + 32 * i;
-                    v[i] = (row < p.M) ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.K + kb * BK) + c)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (!bar_wait(bar_empty + 8 * stage, ((it / NSTAGE) & 1) ^ 1, p.err)) { alive = false; break; }
-                unsigned char* abig = smem + SMEM_A + stage * 2 * KBLK_BYTES;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 b = make_float4(tf32_big(v[i].x), tf32_big(v[i].y), tf32_big(v[i].z), tf32_big(v[i].w));
-                    const float4 s = make_float4(v[i].x - b.x, v[i].y - b.y, v[i].z - b.z, v[i].w - b.w);
-                    const int off = ((r32 >> 3) + 4 * i) * 1024 + rr * 128 + ((c ^ rr) << 4);
-                    *reinterpret_cast<float4*>(abig + off) = b;
-                    *reinterpret_cast<float4*>(abig + KBLK_BYTES + off) = s;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                bar_arrive(bar_full + 8 * stage);
+            for (int i = 0; i < 4; ++i) {
+                const int64_t row = tile * BM + r32 + 32 * i;
+                v[i] = (item < total && row < p.M)
+                           ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.K + kb * BK) + c)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        float4 v[4], vn[4];
+        fetch(0, v);
+        for (int64_t it = 0; it < total; ++it) {
+            fetch(it + 1, vn);
+            const int stage = (int)(it % NSTAGE);
+            if (!bar_wait(bar_empty + 8 * stage, (uint32_t)(((it / NSTAGE) & 1) ^ 1), p.err)) break;
+            unsigned char* abig = smem + SMEM_A + stage * 2 * KBLK_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 b = make_float4(tf32_big(v[i].x), tf32_big(v[i].y), tf32_big(v[i].z), tf32_big(v[i].w));
+                const float4 s = make_float4(v[i].x - b.x, v[i].y - b.y, v[i].z - b.z, v[i].w - b.w);
+                const int off = ((r32 >> 3) + 4 * i) * 1024 + rr * 128 + ((c ^ rr) << 4);
+                *reinterpret_cast<float4*>(abig + off) = b;
+                *reinterpret_cast<float4*>(abig + KBLK_BYTES + off) = s;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(bar_full + 8 * stage);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = vn[i];
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
@@ -239,6 +247,166 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
 }
 }  // namespace tc
 
+// =====================================================================================================================
+// dW = dPre^T * X  (the weight pullback of the dense layer):  dW[i][j] = sum_r dPre[r][i] * X[r][j],  r over all N rows.
+// Both operands are "MN-major" in memory (the reduction index r is the slow one), which UMMA reads directly:
+// canonical SWIZZLE_128B MN-major atoms are 8 k-rows x 128 B (32 consecutive m), LBO = stride between atoms along M/N,
+// SBO = stride between 8-k groups — the loaders are a straight copy + split + swizzle of the global rows.
+// Split-K: every CTA reduces a contiguous range of rows into its own TMEM accumulator and writes a (128 x Din) partial;
+// a second kernel adds the partials in CTA order (deterministic).
+// =====================================================================================================================
+namespace tcw {
+using namespace tc;
+constexpr int WSTAGE = 3;
+constexpr int IMG = 32 * 512;                 // one 32-row image of a 128-float-wide operand: 16 KB
+constexpr int STAGE_BYTES = 4 * IMG;          // dPre big/small, X big/small
+constexpr int SMEM_BARW = WSTAGE * STAGE_BYTES;
+constexpr int SMEM_TOTALW = SMEM_BARW + 128;
+
+struct ParamsW {
+    const float* __restrict__ dpre;   // [M][128]
+    const float* __restrict__ x;      // [M][Din]
+    float* __restrict__ partial;      // [grid][128][Din]
+    int64_t M, rows_per_cta;
+    int Din;
+    int* err;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) dw_tf32x3_kernel(const ParamsW p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = s_u32(smem);
+    const uint32_t bar_full = sbase + SMEM_BARW, bar_empty = bar_full + 8 * WSTAGE, bar_tfull = bar_empty + 8 * WSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BARW + 8 * (2 * WSTAGE + 1));
+    const int nfB = p.Din >> 2;                   // float4 per row of X
+    const int naB = p.Din >> 5;                   // 32-float atoms along N
+    const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+    const int64_t r_end = (r_begin + p.rows_per_cta < p.M) ? r_begin + p.rows_per_cta : p.M;
+    const int64_t nblk = (r_end > r_begin) ? (r_end - r_begin + 31) / 32 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < WSTAGE; ++s) { bar_init(bar_full + 8 * s, LOADERS); bar_init(bar_empty + 8 * s, 1); }
+        bar_init(bar_tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ---- loaders: 32 rows of dPre (128 floats) and of X (Din floats) per stage, straight copy + split + swizzle
+        auto fetch = [&](int64_t blk, float4* va, float4* vb) {
+            const int64_t r0 = r_begin + blk * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = tid + 256 * i;
+                const int ka = idx >> 5, fa = idx & 31;
+                const int64_t ra = r0 + ka;
+                va[i] = (blk < nblk && ra < r_end) ? __ldg(reinterpret_cast<const float4*>(p.dpre + (size_t)ra * 128) + fa)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int kb = idx / nfB, fb = idx - kb * nfB;
+                const int64_t rb = r0 + kb;
+                vb[i] = (blk < nblk && kb < 32 && rb < r_end) ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)rb * p.Din) + fb)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 va[4], vb[4], na[4], nb[4];
+        fetch(0, va, vb);
+        for (int64_t blk = 0; blk < nblk; ++blk) {
+            fetch(blk + 1, na, nb);
+            const int stage = (int)(blk % WSTAGE);
+            if (!bar_wait(bar_empty + 8 * stage, (uint32_t)(((blk / WSTAGE) & 1) ^ 1), p.err)) break;
+            unsigned char* st = smem + stage * STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = tid + 256 * i;
+                {
+                    const int k = idx >> 5, f = idx & 31;
+                    const int off = ((k >> 3) * 4 + (f >> 3)) * 1024 + (k & 7) * 128 + (((f & 7) ^ (k & 7)) << 4);
+                    const float4 b = make_float4(tf32_big(va[i].x), tf32_big(va[i].y), tf32_big(va[i].z), tf32_big(va[i].w));
+                    *reinterpret_cast<float4*>(st + off) = b;
+                    *reinterpret_cast<float4*>(st + IMG + off) = make_float4(va[i].x - b.x, va[i].y - b.y, va[i].z - b.z, va[i].w - b.w);
+                }
+                {
+                    const int k = idx / nfB, f = idx - k * nfB;
+                    if (k < 32) {
+                        const int off = ((k >> 3) * naB + (f >> 3)) * 1024 + (k & 7) * 128 + (((f & 7) ^ (k & 7)) << 4);
+                        const float4 b = make_float4(tf32_big(vb[i].x), tf32_big(vb[i].y), tf32_big(vb[i].z), tf32_big(vb[i].w));
+                        *reinterpret_cast<float4*>(st + 2 * IMG + off) = b;
+                        *reinterpret_cast<float4*>(st + 3 * IMG + off) = make_float4(vb[i].x - b.x, vb[i].y - b.y, vb[i].z - b.z, vb[i].w - b.w);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(bar_full + 8 * stage);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { va[i] = na[i]; vb[i] = nb[i]; }
+        }
+    } else if (warp == MMA_WARP) {
+        // M = 128 (rows of dW), N = Din, both operands MN-major (bits 15, 16)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.Din >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int64_t blk = 0; blk < nblk; ++blk) {
+            const int stage = (int)(blk % WSTAGE);
+            if (!bar_wait(bar_full + 8 * stage, (uint32_t)((blk / WSTAGE) & 1), p.err)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a_big = sbase + stage * STAGE_BYTES, a_small = a_big + IMG, b_big = a_big + 2 * IMG, b_small = a_big + 3 * IMG;
+#pragma unroll
+                for (int kg = 0; kg < 4; ++kg) {               // 4 groups of 8 rows (MMA K = 8)
+                    const uint32_t ao = kg * 4 * 1024, bo = kg * naB * 1024;
+                    umma_tf32(tmem_base, umma_desc_mn(a_small + ao, 4 * 1024), umma_desc_mn(b_big + bo, naB * 1024), idesc, (blk | kg) != 0);
+                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 1024), umma_desc_mn(b_small + bo, naB * 1024), idesc, 1u);
+                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 1024), umma_desc_mn(b_big + bo, naB * 1024), idesc, 1u);
+                }
+                umma_commit(bar_empty + 8 * stage);
+                if (blk == nblk - 1) umma_commit(bar_tfull);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- epilogue: the CTA's partial (row i of dW = TMEM lane i)
+        const int q = warp & 3;
+        float* prow = p.partial + ((size_t)blockIdx.x * 128 + q * 32 + lane) * p.Din;
+        if (nblk == 0) {
+            for (int c0 = 0; c0 < p.Din; c0 += 4) *reinterpret_cast<float4*>(prow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (bar_wait(bar_tfull, 0, p.err)) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c0 = 0; c0 < p.Din; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+}
+
+__global__ void dw_reduce_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int b = 0; b < nparts; ++b) acc += partial[(size_t)b * n + i];     // fixed order: deterministic
+    dW[i] = acc;
+}
+}  // namespace tcw
+
 static int* g_tc_err = nullptr;
 int g_tc_enabled = 1;
 
@@ -265,6 +433,38 @@ int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, i
     const int64_t ntiles = ceil_div(M, tc::BM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
     tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(p);
+    GNNB_LAUNCHED();
+    return GNNB_OK;
+}
+
+// dW (Dout = 128, Din in {32, 64, 96, 128}); GNNB_EUNSUPPORTED for anything else
+int dw_tf32x3(const float* dpre, const float* x, int64_t M, int64_t Din, int64_t Dout, float* dW, cudaStream_t st) {
+    if (!g_tc_enabled) return GNNB_EUNSUPPORTED;
+    if (Dout != 128 || Din % 32 != 0 || Din > 128 || Din < 32) return GNNB_EUNSUPPORTED;
+    if (((uintptr_t)dpre & 15) || ((uintptr_t)x & 15) || ((uintptr_t)dW & 15)) return GNNB_EUNSUPPORTED;
+    static bool configured = false;
+    static int nsm = 0;
+    static float* partial = nullptr;
+    if (!configured) {
+        GNNB_CUDA(cudaFuncSetAttribute(tcw::dw_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcw::SMEM_TOTALW));
+        int dev = 0;
+        GNNB_CUDA(cudaGetDevice(&dev));
+        GNNB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        GNNB_CUDA(cudaMalloc(&partial, sizeof(float) * (size_t)nsm * 128 * 128));
+        if (!g_tc_err) { GNNB_CUDA(cudaMalloc(&g_tc_err, sizeof(int))); GNNB_CUDA(cudaMemset(g_tc_err, 0, sizeof(int))); }
+        configured = true;
+    }
+    if (M == 0) { GNNB_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)(Dout * Din), st)); return GNNB_OK; }
+    tcw::ParamsW p;
+    p.dpre = dpre; p.x = x; p.partial = partial; p.M = M; p.Din = (int)Din; p.err = g_tc_err;
+    int64_t rpc = ceil_div(M, nsm);
+    rpc = ceil_div(rpc, 32) * 32;
+    p.rows_per_cta = rpc;
+    const int grid = (int)ceil_div(M, rpc);
+    tcw::dw_tf32x3_kernel<<<grid, tc::THREADS, tcw::SMEM_TOTALW, st>>>(p);
+    GNNB_LAUNCHED();
+    const int n = (int)(128 * Din);
+    tcw::dw_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, grid, n, dW);
     GNNB_LAUNCHED();
     return GNNB_OK;
 }
