@@ -249,9 +249,11 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
 
 // =====================================================================================================================
 // dW = dPre^T * X  (the weight pullback of the dense layer):  dW[i][j] = sum_r dPre[r][i] * X[r][j],  r over all N rows.
-// Both operands are "MN-major" in memory (the reduction index r is the slow one), which UMMA reads directly:
-// canonical SWIZZLE_128B MN-major atoms are 8 k-rows x 128 B (32 consecutive m), LBO = stride between atoms along M/N,
-// SBO = stride between 8-k groups — the loaders are a straight copy + split + swizzle of the global rows.
+// Both operands are "MN-major" in memory (the reduction index r is the slow one), which UMMA reads directly.  For
+// MN-major tf32 the only shared-memory layout is SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom): atoms of
+// 4 k-rows x 128 B (32 consecutive m), the 32 B chunk index of a row XORed with the row index (Swizzle<2,5,2> on the
+// byte address); LBO = stride between atoms along M/N, SBO = stride between 4-k groups (one K = 8 MMA spans two).
+// The loaders are a straight copy + split + swizzle of the global rows.
 // Split-K: every CTA reduces a contiguous range of rows into its own TMEM accumulator and writes a (128 x Din) partial;
 // a second kernel adds the partials in CTA order (deterministic).
 // =====================================================================================================================
@@ -273,8 +275,13 @@ struct ParamsW {
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);          // layout type 1 = SWIZZLE_128B_BASE32B
+}
+// byte offset of float4 number f4 of k-row k inside a 32-row image that is `na` 32-float atoms wide
+__device__ __forceinline__ int mn_off(int k, int f4, int na) {
+    const int f = f4 & 7, kr = k & 3;
+    return ((k >> 2) * na + (f4 >> 3)) * 512 + kr * 128 + ((((f >> 1) ^ kr)) << 5) + ((f & 1) << 4);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) dw_tf32x3_kernel(const ParamsW p) {
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tf32x3_kernel(const ParamsW p) 
                 const int idx = tid + 256 * i;
                 {
                     const int k = idx >> 5, f = idx & 31;
-                    const int off = ((k >> 3) * 4 + (f >> 3)) * 1024 + (k & 7) * 128 + (((f & 7) ^ (k & 7)) << 4);
+                    const int off = mn_off(k, f, 4);
                     const float4 b = make_float4(tf32_big(va[i].x), tf32_big(va[i].y), tf32_big(va[i].z), tf32_big(va[i].w));
                     *reinterpret_cast<float4*>(st + off) = b;
                     *reinterpret_cast<float4*>(st + IMG + off) = make_float4(va[i].x - b.x, va[i].y - b.y, va[i].z - b.z, va[i].w - b.w);
@@ -340,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tf32x3_kernel(const ParamsW p) 
                 {
                     const int k = idx / nfB, f = idx - k * nfB;
                     if (k < 32) {
-                        const int off = ((k >> 3) * naB + (f >> 3)) * 1024 + (k & 7) * 128 + (((f & 7) ^ (k & 7)) << 4);
+                        const int off = mn_off(k, f, naB);
                         const float4 b = make_float4(tf32_big(vb[i].x), tf32_big(vb[i].y), tf32_big(vb[i].z), tf32_big(vb[i].w));
                         *reinterpret_cast<float4*>(st + 2 * IMG + off) = b;
                         *reinterpret_cast<float4*>(st + 3 * IMG + off) = make_float4(vb[i].x - b.x, vb[i].y - b.y, vb[i].z - b.z, vb[i].w - b.w);
@@ -364,10 +371,10 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tf32x3_kernel(const ParamsW p) 
                 const uint32_t a_big = sbase + stage * STAGE_BYTES, a_small = a_big + IMG, b_big = a_big + 2 * IMG, b_small = a_big + 3 * IMG;
 #pragma unroll
                 for (int kg = 0; kg < 4; ++kg) {               // 4 groups of 8 rows (MMA K = 8)
-                    const uint32_t ao = kg * 4 * 1024, bo = kg * naB * 1024;
-                    umma_tf32(tmem_base, umma_desc_mn(a_small + ao, 4 * 1024), umma_desc_mn(b_big + bo, naB * 1024), idesc, (blk | kg) != 0);
-                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 1024), umma_desc_mn(b_small + bo, naB * 1024), idesc, 1u);
-                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 1024), umma_desc_mn(b_big + bo, naB * 1024), idesc, 1u);
+                    const uint32_t ao = kg * 2 * 4 * 512, bo = kg * 2 * naB * 512;      // two 4-row K-atoms per MMA
+                    umma_tf32(tmem_base, umma_desc_mn(a_small + ao, 4 * 512), umma_desc_mn(b_big + bo, naB * 512), idesc, (blk | kg) != 0);
+                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 512), umma_desc_mn(b_small + bo, naB * 512), idesc, 1u);
+                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 512), umma_desc_mn(b_big + bo, naB * 512), idesc, 1u);
                 }
                 umma_commit(bar_empty + 8 * stage);
                 if (blk == nblk - 1) umma_commit(bar_tfull);
