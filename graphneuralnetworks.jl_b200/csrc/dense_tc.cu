@@ -259,10 +259,16 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
 // =====================================================================================================================
 namespace tcw {
 using namespace tc;
-constexpr int WSTAGE = 3;
+// The TMEM accumulator does not round to nearest: a long accumulation chain drifts by ~2^-25.7 of the running sum per
+// MMA (measured: 5.3e-6 relative after 264 accumulations).  The chain is therefore cut every FLUSH row blocks (128
+// rows = 48 accumulations); the epilogue warps add each short partial into an fp32 shared-memory sum with ordinary
+// round-to-nearest adds while the MMA warp already fills the other TMEM accumulator.
+constexpr int WSTAGE = 2;
+constexpr int FLUSH = 4;                      // row blocks (of 32 rows) per accumulation chain
 constexpr int IMG = 32 * 512;                 // one 32-row image of a 128-float-wide operand: 16 KB
 constexpr int STAGE_BYTES = 4 * IMG;          // dPre big/small, X big/small
-constexpr int SMEM_BARW = WSTAGE * STAGE_BYTES;
+constexpr int SMEM_ACC = WSTAGE * STAGE_BYTES;            // fp32 running sum, [col][row] (conflict-free per warp)
+constexpr int SMEM_BARW = SMEM_ACC + 128 * 128 * 4;
 constexpr int SMEM_TOTALW = SMEM_BARW + 128;
 
 struct ParamsW {
@@ -288,21 +294,24 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tf32x3_kernel(const ParamsW p) 
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = s_u32(smem);
-    const uint32_t bar_full = sbase + SMEM_BARW, bar_empty = bar_full + 8 * WSTAGE, bar_tfull = bar_empty + 8 * WSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BARW + 8 * (2 * WSTAGE + 1));
+    const uint32_t bar_full = sbase + SMEM_BARW, bar_empty = bar_full + 8 * WSTAGE;
+    const uint32_t bar_tfull = bar_empty + 8 * WSTAGE, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BARW + 8 * (2 * WSTAGE + 4));
+    float* sacc = reinterpret_cast<float*>(smem + SMEM_ACC);
     const int nfB = p.Din >> 2;                   // float4 per row of X
     const int naB = p.Din >> 5;                   // 32-float atoms along N
     const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
     const int64_t r_end = (r_begin + p.rows_per_cta < p.M) ? r_begin + p.rows_per_cta : p.M;
     const int64_t nblk = (r_end > r_begin) ? (r_end - r_begin + 31) / 32 : 0;
+    const int64_t ngroups = (nblk + FLUSH - 1) / FLUSH;
 
     if (tid == 0) {
         for (int s = 0; s < WSTAGE; ++s) { bar_init(bar_full + 8 * s, LOADERS); bar_init(bar_empty + 8 * s, 1); }
-        bar_init(bar_tfull, 1);
+        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8 * a, 1); bar_init(bar_tempty + 8 * a, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -364,45 +373,62 @@ __global__ void __launch_bounds__(THREADS, 1) dw_tf32x3_kernel(const ParamsW p) 
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(p.Din >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         for (int64_t blk = 0; blk < nblk; ++blk) {
+            const int64_t grp = blk / FLUSH;
+            const int acc = (int)(grp & 1);
+            const bool first = (blk % FLUSH) == 0, last = (blk % FLUSH) == FLUSH - 1 || blk == nblk - 1;
+            if (first) {
+                if (!bar_wait(bar_tempty + 8 * acc, (uint32_t)(((grp >> 1) & 1) ^ 1), p.err)) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             const int stage = (int)(blk % WSTAGE);
             if (!bar_wait(bar_full + 8 * stage, (uint32_t)((blk / WSTAGE) & 1), p.err)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
+                const uint32_t tmem_d = tmem_base + acc * 128;
                 const uint32_t a_big = sbase + stage * STAGE_BYTES, a_small = a_big + IMG, b_big = a_big + 2 * IMG, b_small = a_big + 3 * IMG;
 #pragma unroll
-                for (int kg = 0; kg < 4; ++kg) {               // 4 groups of 8 rows (MMA K = 8)
-                    const uint32_t ao = kg * 2 * 4 * 512, bo = kg * 2 * naB * 512;      // two 4-row K-atoms per MMA
-                    umma_tf32(tmem_base, umma_desc_mn(a_small + ao, 4 * 512), umma_desc_mn(b_big + bo, naB * 512), idesc, (blk | kg) != 0);
-                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 512), umma_desc_mn(b_small + bo, naB * 512), idesc, 1u);
-                    umma_tf32(tmem_base, umma_desc_mn(a_big + ao, 4 * 512), umma_desc_mn(b_big + bo, naB * 512), idesc, 1u);
+                for (int kg = 0; kg < 4; ++kg) {               // 4 groups of 8 rows (MMA K = 8 = two 4-row K-atoms)
+                    const uint32_t ao = kg * 2 * 4 * 512, bo = kg * 2 * naB * 512;
+                    umma_tf32(tmem_d, umma_desc_mn(a_small + ao, 4 * 512), umma_desc_mn(b_big + bo, naB * 512), idesc, (first && kg == 0) ? 0u : 1u);
+                    umma_tf32(tmem_d, umma_desc_mn(a_big + ao, 4 * 512), umma_desc_mn(b_small + bo, naB * 512), idesc, 1u);
+                    umma_tf32(tmem_d, umma_desc_mn(a_big + ao, 4 * 512), umma_desc_mn(b_big + bo, naB * 512), idesc, 1u);
                 }
                 umma_commit(bar_empty + 8 * stage);
-                if (blk == nblk - 1) umma_commit(bar_tfull);
+                if (last) umma_commit(bar_tfull + 8 * acc);
             }
             __syncwarp();
         }
     } else {
-        // ---- epilogue: the CTA's partial (row i of dW = TMEM lane i)
+        // ---- epilogue: add every short chain into the fp32 shared-memory sum, then write this CTA's partial
         const int q = warp & 3;
-        float* prow = p.partial + ((size_t)blockIdx.x * 128 + q * 32 + lane) * p.Din;
-        if (nblk == 0) {
-            for (int c0 = 0; c0 < p.Din; c0 += 4) *reinterpret_cast<float4*>(prow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else if (bar_wait(bar_tfull, 0, p.err)) {
+        const int row = q * 32 + lane;                             // row i of dW = TMEM lane i
+        for (int64_t grp = 0; grp < ngroups; ++grp) {
+            const int acc = (int)(grp & 1);
+            if (!bar_wait(bar_tfull + 8 * acc, (uint32_t)((grp >> 1) & 1), p.err)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int c0 = 0; c0 < p.Din; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                           __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                for (int j = 0; j < 32; ++j) {
+                    float* a = sacc + (c0 + j) * 128 + row;
+                    *a = (grp == 0) ? __uint_as_float(r[j]) : *a + __uint_as_float(r[j]);
+                }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(bar_tempty + 8 * acc);
+        }
+        float* prow = p.partial + ((size_t)blockIdx.x * 128 + row) * p.Din;
+        for (int c0 = 0; c0 < p.Din; c0 += 4) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ngroups > 0) o = make_float4(sacc[(c0 + 0) * 128 + row], sacc[(c0 + 1) * 128 + row], sacc[(c0 + 2) * 128 + row], sacc[(c0 + 3) * 128 + row]);
+            *reinterpret_cast<float4*>(prow + c0) = o;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
 __global__ void dw_reduce_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dW) {

@@ -2,7 +2,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gnnb200 as gnn
 lib = gnn._lib.lib
-for (N, Din, Dout) in ((37, 128, 128), (4096, 128, 128), (4096, 64, 128), (100000, 32, 128)):
+for (N, Din, Dout) in ((37, 128, 128), (4096, 64, 128), (100000, 32, 128), (1000000, 128, 128), (10000000, 128, 128)):
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(N, Din, device="cuda", generator=g)
     W = torch.randn(Dout, Din, device="cuda", generator=g) / Din ** 0.5

@@ -651,7 +651,8 @@ def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
 
 # --------------------------------------------------------------------------------------------- dense layer part
 @pytest.mark.parametrize("N,Din,Dout", [(1000, 128, 128), (777, 16, 8), (5000, 64, 256), (33, 1432, 16), (0, 8, 8),
-                                        (4096, 64, 128), (130000, 128, 64), (300, 32, 16), (129, 96, 48), (1, 128, 128)])
+                                        (4096, 64, 128), (130000, 128, 64), (300, 32, 16), (129, 96, 48), (1, 128, 128),
+                                        (400000, 128, 128), (70001, 96, 128)])
 @pytest.mark.parametrize("relu_flag,with_bias", [(1, True), (0, True), (1, False), (0, False)])
 @pytest.mark.parametrize("emulate", [1, 0])
 def test_linear_c_abi(gnn, N, Din, Dout, relu_flag, with_bias, emulate):
