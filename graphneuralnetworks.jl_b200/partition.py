@@ -309,16 +309,34 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks):
         yh = torch.empty(dg.n_local, D, pin_memory=True)
         dxh = torch.empty(dg.n_local, D, pin_memory=True)
 
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+
         def step_host():
-            xd = gnn.unrows(xh.to(dev, non_blocking=True)).requires_grad_(True)
+            # uploads on s_in, downloads on s_out (PCIe is full duplex), compute on the main stream
+            with torch.cuda.stream(s_in):
+                xd_raw = xh.to(dev, non_blocking=True)
+                ev_x = torch.cuda.Event(); ev_x.record(s_in)
+                dyd_raw = dyh.to(dev, non_blocking=True)
+                ev_dy = torch.cuda.Event(); ev_dy.record(s_in)
+            main.wait_event(ev_x)
+            xd = gnn.unrows(xd_raw).requires_grad_(True)
             layer.weight.grad = None
             layer.bias.grad = None
             y = dist_gcn_conv(layer, dg, xd)
-            yh.copy_(gnn.rows(y.detach()), non_blocking=True)
-            y.backward(gnn.unrows(dyh.to(dev, non_blocking=True)))
-            dxh.copy_(gnn.rows(xd.grad), non_blocking=True)
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                yh.copy_(gnn.rows(y.detach()), non_blocking=True)
+            main.wait_event(ev_dy)
+            y.backward(gnn.unrows(dyd_raw))
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                dxh.copy_(gnn.rows(xd.grad), non_blocking=True)
             dist.all_reduce(layer.weight.grad)
-            return layer.weight.grad.cpu()
+            wg = layer.weight.grad.cpu()
+            main.wait_stream(s_out)
+            xd_raw.record_stream(main); dyd_raw.record_stream(main)
+            return wg
 
         ke = max(2, min(args.steps, 5))
         step_host()
