@@ -96,6 +96,12 @@ _SIGS = {
     "gnnb_dense_emulation_active": (_int, []),
     "gnnb_gather_rows": (_int, [_vp, _i64, _f32p, _i64, _f32p, _vp]),
     "gnnb_propagate_halo": (_int, [_vp, _int, _int, _f32p, _f32p, _i64, _f32p, _f32p, _f32p, _i64, _f32p, _vp]),
+    "gnnb_dev_alloc": (_int, [C.POINTER(_vp), _i64]),
+    "gnnb_dev_free": (_int, [_vp]),
+    "gnnb_ipc_get_handle": (_int, [_vp, _vp]),
+    "gnnb_ipc_open_handle": (_int, [_vp, C.POINTER(_vp)]),
+    "gnnb_ipc_close_handle": (_int, [_vp]),
+    "gnnb_halo_push": (_int, [_vp, _vp, _vp, _vp, _int, _f32p, _i64, _vp]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_gcn_propagate_host": (_int, [_vp, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_rmat_edges": (_int, [_i64, _i64, C.c_uint64, _vp, _vp, _vp]),

@@ -101,6 +101,7 @@ class _Shard:
         self.send_counts = send_counts
         self.plan = plan
         self.num_edges = int(d["row"].numel())
+        self.push = None           # per-D state of the peer-to-peer push path (_PushState)
 
 
 class DistGraph:
@@ -157,6 +158,66 @@ class DistGraph:
                                input_split_sizes=shard.send_counts, group=self.group)
         return recv
 
+    # -- halo exchange, push path: one kernel writes the requested rows into every peer's halo buffer over NVLink
+    def _push_state(self, shard: _Shard, D: int):
+        st = shard.push.get(D) if shard.push else None
+        if st is not None:
+            return st
+        if shard.push is None:
+            shard.push = {}
+        dev = self.device
+        world, rank = self.world, self.rank
+        # where my rows start inside every peer's halo buffer: that peer's recv_counts summed over owners < me
+        all_recv = [None] * world
+        dist.all_gather_object(all_recv, list(shard.recv_counts), group=self.group)
+        row0 = [int(sum(all_recv[q][:rank])) for q in range(world)]
+        bufs, handles = [], []
+        with torch.cuda.device(dev):
+            for _ in range(2):                                   # double buffer: pass k+1 never overwrites what pass k reads
+                ptr = C.c_void_p()
+                _lib.check(lib.gnnb_dev_alloc(C.byref(ptr), max(shard.n_halo, 1) * D * 4))
+                h = (C.c_ubyte * 64)()
+                _lib.check(lib.gnnb_ipc_get_handle(ptr, h))
+                bufs.append(ptr.value)
+                handles.append(bytes(h))
+        all_handles = [None] * world
+        dist.all_gather_object(all_handles, handles, group=self.group)
+        peer_ptrs = [[0] * world, [0] * world]
+        with torch.cuda.device(dev):
+            for q in range(world):
+                if q == rank or shard.send_counts[q] == 0:
+                    continue
+                for b in range(2):
+                    pp = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(all_handles[q][b])
+                    _lib.check(lib.gnnb_ipc_open_handle(hb, C.byref(pp)))
+                    peer_ptrs[b][q] = pp.value
+        seg = [0]
+        for q in range(world):
+            seg.append(seg[-1] + int(shard.send_counts[q]))
+        st = {"bufs": bufs, "peer": peer_ptrs, "row0": (C.c_int64 * world)(*row0), "seg": (C.c_int64 * (world + 1))(*seg),
+              "peer_c": [(C.c_void_p * world)(*[C.c_void_p(v) for v in peer_ptrs[b]]) for b in range(2)], "turn": 0,
+              "flag": torch.zeros(1, device=dev)}
+        shard.push[D] = st
+        dist.barrier(group=self.group)
+        return st
+
+    def halo_ptr(self, shard: _Shard, x_rows: torch.Tensor) -> int:
+        """device pointer of this rank's halo rows for `x_rows` (valid until the next-but-one call for this shard)"""
+        if self.world == 1 or os.environ.get("GNNB_HALO", "push") != "push":
+            t = self.halo(shard, x_rows)
+            self._keep = t                                      # keep the NCCL receive buffer alive for the kernel
+            return t.data_ptr()
+        D = x_rows.shape[1]
+        st = self._push_state(shard, D)
+        b = st["turn"]
+        st["turn"] ^= 1
+        with torch.cuda.device(self.device):
+            _lib.check(lib.gnnb_halo_push(shard.send_idx.data_ptr(), st["seg"], st["peer_c"][b], st["row0"], self.world,
+                                          x_rows.data_ptr(), D, _stream(self.device)))
+        dist.all_reduce(st["flag"], group=self.group)           # every rank's push kernel precedes its part of this collective
+        return st["bufs"][b]
+
     def gcn_c(self):
         """c = 1/sqrt(in-degree) of the owned nodes (exact: rowptr differences of the forward shard), plus the
         halo copies the two shards need.  Computed once."""
@@ -172,11 +233,11 @@ class DistGraph:
 
     def propagate(self, shard: _Shard, x_rows: torch.Tensor, cs, ct, aggr=_lib.SUM) -> torch.Tensor:
         D = x_rows.shape[1]
-        halo = self.halo(shard, x_rows)
+        hptr = self.halo_ptr(shard, x_rows)
         out = torch.empty_like(x_rows)
         with torch.cuda.device(self.device):
             _lib.check(lib.gnnb_propagate_halo(shard.plan.h, _lib.COPY_XJ, aggr, x_rows.data_ptr(),
-                                               halo.data_ptr() if shard.n_halo else None, shard.n_local, None,
+                                               hptr if shard.n_halo else None, shard.n_local, None,
                                                _ptr(cs), _ptr(ct), D, out.data_ptr(), _stream(self.device)))
         return out
 
@@ -285,11 +346,11 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks):
     kms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
     # halo exchange alone
     for _ in range(2):
-        dg.halo(dg.fwd, xr)
+        dg.halo_ptr(dg.fwd, xr)
     torch.cuda.synchronize(); dist.barrier()
     ev0.record()
     for _ in range(args.steps):
-        dg.halo(dg.fwd, xr)
+        dg.halo_ptr(dg.fwd, xr)
     ev1.record()
     torch.cuda.synchronize()
     hms = ev0.elapsed_time(ev1) / args.steps
@@ -362,6 +423,7 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks):
             "config": {"workload": f"GCNConv {D}->{D} (add_self_loops, relu, bias) fwd+bwd on RMAT N={n} E={E} seed {seed} "
                                    f"(BASELINE configs[1]), node-partitioned over {world} GPUs, NCCL halo exchange",
                        "parallelism": f"node-partition x{world}, cost-balanced contiguous ranges",
+                       "halo_exchange": os.environ.get("GNNB_HALO", "push") + (" (one kernel writes rows into peer halo buffers over NVLink, CUDA IPC)" if os.environ.get("GNNB_HALO", "push") == "push" else " (pack kernel + NCCL all_to_all_single)"),
                        "l2": "per-GPU features and halo buffers are far larger than the 126 MB L2",
                        "plan_build_ms": t_plan * 1e3, "chunk_edges": 128,
                        "per_rank": {"kernel_ms": allst[:, 0].tolist(), "halo_exchange_ms": allst[:, 1].tolist(),

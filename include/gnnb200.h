@@ -226,6 +226,21 @@ int gnnb_propagate_halo(gnnb_graph_t g, int msg, int aggr, const float* x_local,
                         int64_t n_local, const float* w, const float* cs, const float* ct, int64_t D,
                         float* out, void* stream);
 
+/* Halo exchange without a staging copy: every rank writes the rows a peer asked for straight into that peer's halo
+ * buffer over NVLink (peer-mapped memory).  gnnb_dev_alloc / gnnb_ipc_* manage exportable device buffers (plain
+ * cudaMalloc + CUDA IPC handles, 64 bytes each, exchanged by the host side); gnnb_halo_push launches ONE kernel:
+ * row k of the send list (grouped by peer: rows [seg_start[p], seg_start[p+1]) go to peer p) is copied from
+ * x[send_idx[k],:] to peer_base[p] + (peer_row0[p] + k - seg_start[p])*D.  seg_start (world+1), peer_base (world),
+ * peer_row0 (world) are HOST arrays.  Completion on the peers is published by a collective the caller issues on the
+ * same stream afterwards. */
+int gnnb_dev_alloc(void** p, int64_t bytes);
+int gnnb_dev_free(void* p);
+int gnnb_ipc_get_handle(void* p, unsigned char* handle64);
+int gnnb_ipc_open_handle(const unsigned char* handle64, void** p);
+int gnnb_ipc_close_handle(void* p);
+int gnnb_halo_push(const int32_t* send_idx_dev, const int64_t* seg_start_host, const void* const* peer_base_host,
+                   const int64_t* peer_row0_host, int world, const float* x, int64_t D, void* stream);
+
 /* ------------------------------------------------------ host-buffer entries
  * The reference-facing call with HOST arrays (what a CPU-array caller of `propagate` has): copies
  * x (and w) to the device, runs the fused pass, copies `out` back; synchronous.  Used for the
