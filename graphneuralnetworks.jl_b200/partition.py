@@ -160,46 +160,58 @@ class DistGraph:
 
     # -- halo exchange, push path: one kernel writes the requested rows into every peer's halo buffer over NVLink
     def _push_state(self, shard: _Shard, D: int):
-        st = shard.push.get(D) if shard.push else None
-        if st is not None:
-            return st
+        """Peer-mapped double-buffered halo buffers for rows of D floats (built once per shard and D).  Every rank runs
+        the same collectives whatever happens locally; if any rank fails to allocate / export / map, ALL ranks fall
+        back to the NCCL exchange (returns None)."""
         if shard.push is None:
             shard.push = {}
-        dev = self.device
-        world, rank = self.world, self.rank
-        # where my rows start inside every peer's halo buffer: that peer's recv_counts summed over owners < me
+        if D in shard.push:
+            return shard.push[D]
+        dev, world, rank = self.device, self.world, self.rank
+        ok = 1
         all_recv = [None] * world
         dist.all_gather_object(all_recv, list(shard.recv_counts), group=self.group)
-        row0 = [int(sum(all_recv[q][:rank])) for q in range(world)]
+        row0 = [int(sum(all_recv[q][:rank])) for q in range(world)]   # where my rows start in every peer's halo buffer
         bufs, handles = [], []
-        with torch.cuda.device(dev):
-            for _ in range(2):                                   # double buffer: pass k+1 never overwrites what pass k reads
-                ptr = C.c_void_p()
-                _lib.check(lib.gnnb_dev_alloc(C.byref(ptr), max(shard.n_halo, 1) * D * 4))
-                h = (C.c_ubyte * 64)()
-                _lib.check(lib.gnnb_ipc_get_handle(ptr, h))
-                bufs.append(ptr.value)
-                handles.append(bytes(h))
+        try:
+            with torch.cuda.device(dev):
+                for _ in range(2):                               # double buffer: pass k+1 never overwrites what pass k reads
+                    ptr = C.c_void_p()
+                    _lib.check(lib.gnnb_dev_alloc(C.byref(ptr), max(shard.n_halo, 1) * D * 4))
+                    h = (C.c_ubyte * 64)()
+                    _lib.check(lib.gnnb_ipc_get_handle(ptr, h))
+                    bufs.append(ptr.value)
+                    handles.append(bytes(h))
+        except Exception:
+            ok = 0
+            handles = [bytes(64), bytes(64)]
         all_handles = [None] * world
         dist.all_gather_object(all_handles, handles, group=self.group)
         peer_ptrs = [[0] * world, [0] * world]
-        with torch.cuda.device(dev):
-            for q in range(world):
-                if q == rank or shard.send_counts[q] == 0:
-                    continue
-                for b in range(2):
-                    pp = C.c_void_p()
-                    hb = (C.c_ubyte * 64).from_buffer_copy(all_handles[q][b])
-                    _lib.check(lib.gnnb_ipc_open_handle(hb, C.byref(pp)))
-                    peer_ptrs[b][q] = pp.value
+        try:
+            with torch.cuda.device(dev):
+                for q in range(world):
+                    if q == rank or shard.send_counts[q] == 0:
+                        continue
+                    for b in range(2):
+                        pp = C.c_void_p()
+                        hb = (C.c_ubyte * 64).from_buffer_copy(all_handles[q][b])
+                        _lib.check(lib.gnnb_ipc_open_handle(hb, C.byref(pp)))
+                        peer_ptrs[b][q] = pp.value
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            shard.push[D] = None
+            return None
         seg = [0]
         for q in range(world):
             seg.append(seg[-1] + int(shard.send_counts[q]))
-        st = {"bufs": bufs, "peer": peer_ptrs, "row0": (C.c_int64 * world)(*row0), "seg": (C.c_int64 * (world + 1))(*seg),
+        st = {"bufs": bufs, "row0": (C.c_int64 * world)(*row0), "seg": (C.c_int64 * (world + 1))(*seg),
               "peer_c": [(C.c_void_p * world)(*[C.c_void_p(v) for v in peer_ptrs[b]]) for b in range(2)], "turn": 0,
               "flag": torch.zeros(1, device=dev)}
         shard.push[D] = st
-        dist.barrier(group=self.group)
         return st
 
     def halo_ptr(self, shard: _Shard, x_rows: torch.Tensor) -> int:
@@ -210,6 +222,10 @@ class DistGraph:
             return t.data_ptr()
         D = x_rows.shape[1]
         st = self._push_state(shard, D)
+        if st is None:                                          # some rank could not set up peer mapping: NCCL for everyone
+            t = self.halo(shard, x_rows)
+            self._keep = t
+            return t.data_ptr()
         b = st["turn"]
         st["turn"] ^= 1
         with torch.cuda.device(self.device):
