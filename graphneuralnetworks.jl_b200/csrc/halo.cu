@@ -11,6 +11,9 @@ struct PushParams {
     float* peer_base[MAX_PEERS];     // halo buffer of every peer (peer-mapped), nullptr for self / unused
     int64_t peer_row0[MAX_PEERS];    // first row inside that buffer that belongs to this rank
     int64_t seg_start[MAX_PEERS + 1];  // send list is grouped by peer: rows [seg_start[p], seg_start[p+1]) go to peer p
+    int64_t stride;                  // multiplicative permutation of the row order (coprime with n_send): every rank writes
+                                     // to all of its peers at the same time instead of peer after peer (all ranks hammering
+                                     // rank 0's inbound links first: measured 395 GB/s at 4 GPUs)
     int world;
 };
 
@@ -20,7 +23,8 @@ __global__ void halo_push_kernel(const PushParams pp, const int32_t* __restrict_
     const int64_t nvec = D / VEC;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_send * nvec) return;
-    const int64_t r = i / nvec, f = (i - r * nvec) * VEC;
+    const int64_t v = i / nvec, f = (i - v * nvec) * VEC;
+    const int64_t r = (int64_t)(((unsigned __int128)v * (unsigned __int128)pp.stride) % (unsigned __int128)n_send);
     int p = 0;
     while (p + 1 < pp.world && r >= pp.seg_start[p + 1]) ++p;       // <= 16 peers: a short scan
     float* dst = pp.peer_base[p] + (size_t)(pp.peer_row0[p] + (r - pp.seg_start[p])) * D + f;
@@ -84,6 +88,11 @@ int gnnb_halo_push(const int32_t* send_idx_dev, const int64_t* seg_start_host, c
     const int64_t n_send = seg_start_host[world];
     if (n_send == 0) return GNNB_OK;
     if (!send_idx_dev || !x) GNNB_FAIL(GNNB_EINVAL, "halo_push: NULL argument");
+    pp.stride = 1;
+    for (int64_t cand : {1000003LL, 999983LL, 15485863LL, 32452843LL}) {
+        if (n_send % cand != 0) { pp.stride = cand % n_send; break; }   // prime not dividing n_send => bijection mod n_send
+    }
+    if (pp.stride == 0) pp.stride = 1;
     cudaStream_t st = (cudaStream_t)stream;
     bool v4 = D % 4 == 0 && !((uintptr_t)x & 15);
     for (int p = 0; p < world; ++p) if ((uintptr_t)pp.peer_base[p] & 15) v4 = false;
