@@ -379,3 +379,69 @@ class SAGEConv(torch.nn.Module):
 
     def forward(self, g: GNNGraph, x: torch.Tensor):
         return sage_conv(self, g, x)
+
+
+# ------------------------------------------------------------------ layers that re-parameterise the same kernels (§8f rank 1)
+def graph_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:102-108: σ.(W1*xi .+ W2*propagate(copy_xj, g, aggr, xj) .+ b)."""
+    check_num_nodes(g, x)
+    xj, xi = expand_srcdst(g, x)
+    m = propagate(copy_xj, g, l.aggr, xj=xj)
+    out = unrows(torch.addmm(rows(xi) @ l.weight1.t(), rows(m), l.weight2.t()))
+    return _sigma(l)(_add_bias(out, _bias(l)))
+
+
+def gin_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:250-256: nn((1 + ϵ) .* xi .+ propagate(copy_xj, g, aggr, xj))."""
+    check_num_nodes(g, x)
+    xj, xi = expand_srcdst(g, x)
+    m = propagate(copy_xj, g, l.aggr, xj=xj)
+    eps = getattr(l, "ϵ", getattr(l, "eps", 0.0))
+    return l.nn((1 + eps) * xi + m)
+
+
+def sgc_conv(l, g: GNNGraph, x: torch.Tensor, edge_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:407-448 (SGConv): k rounds of the normalised GCN propagate around one W; the
+    unweighted case is k launches of the fused kernel (both 1/sqrt(d) scalings folded in)."""
+    if edge_weight is not None:
+        assert edge_weight.numel() == g.num_edges, \
+            f"Wrong number of edge weights (expected {g.num_edges} but given {edge_weight.numel()})"
+    if l.add_self_loops:
+        g = add_self_loops(g)
+        if edge_weight is not None:
+            edge_weight = torch.cat([edge_weight, torch.ones(g.num_nodes, dtype=edge_weight.dtype, device=edge_weight.device)])
+    W = l.weight
+    Dout, Din = W.shape
+    if Dout < Din:
+        x = _linear(l, W, x, False)
+    use_w = bool(getattr(l, "use_edge_weight", False)) and g.w is not None
+    if edge_weight is None and not use_w:
+        plan = g.plan()
+        xr = _f32(rows(x), plan.device)
+        c = _gcn_c(g)
+        for _ in range(int(l.k)):
+            xr = _GCNPropagateFn.apply(xr, plan, c)
+        x = unrows(xr)
+    else:
+        d = degree(g, torch.float32, dir="in", edge_weight=edge_weight if edge_weight is not None else True)
+        c = (1.0 / torch.sqrt(d)).reshape(1, -1)
+        for _ in range(int(l.k)):
+            x = x * c
+            x = (propagate(e_mul_xj, g, operator.add, xj=x, e=edge_weight) if edge_weight is not None
+                 else propagate(w_mul_xj, g, operator.add, xj=x))
+            x = x * c
+    if Dout >= Din:
+        x = _linear(l, W, x, False)
+    return _add_bias(x, _bias(l))
+
+
+def agnn_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:337-352: cosine-similarity attention, neighbourhood softmax, weighted sum."""
+    check_num_nodes(g, x)
+    if l.add_self_loops:
+        g = add_self_loops(g)
+    from .msgpass import xi_dot_xj
+    xn = x / torch.sqrt((x ** 2).sum(dim=0, keepdim=True))
+    cos_dist = apply_edges(xi_dot_xj, g, xi=xn, xj=xn)
+    alpha = softmax_edge_neighbors(g, l.β * cos_dist if hasattr(l, "β") else l.beta * cos_dist)
+    return propagate(lambda xi, xj, a: a * xj, g, operator.add, xj=x, e=alpha)

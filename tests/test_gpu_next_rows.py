@@ -1,0 +1,106 @@
+"""SURVEY.md §8f rows built on the same kernels: graph-level readout (GNNlib/test/utils.jl:13-56 transcribed) and the
+layers that re-parameterise propagate (graph_conv, gin_conv, sgc_conv, agnn_conv) against oracle compositions."""
+import operator
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _batched(gnn, rng, ngraphs=5, n=10, e=60, Dx=2, De=3):
+    gs = []
+    for _ in range(ngraphs):
+        s = rng.integers(1, n + 1, e)
+        t = rng.integers(1, n + 1, e)
+        gs.append(gnn.GNNGraph(s, t, num_nodes=n, ndata={"x": gnn.colmajor(torch.rand(Dx, n))},
+                               edata={"e": gnn.colmajor(torch.rand(De, e))}))
+    return gnn.batch(gs).cuda(), gs
+
+
+def test_reduce_softmax_broadcast(gnn):
+    rng = np.random.default_rng(0)
+    g, gs = _batched(gnn, rng)
+    x, e = g.ndata["x"], g.edata["e"]
+    r = gnn.reduce_nodes(gnn.mean, g, x)
+    assert r.shape == (2, g.num_graphs)
+    assert torch.allclose(r[:, 1].cpu(), gs[1].ndata["x"].mean(dim=1), rtol=1e-6)           # utils.jl:16-17
+    assert torch.equal(gnn.reduce_nodes(gnn.mean, gnn.graph_indicator(g), x), r)             # utils.jl:19-20
+    r = gnn.reduce_edges(gnn.mean, g, e)
+    assert r.shape == (3, g.num_graphs)
+    assert torch.allclose(r[:, 1].cpu(), gs[1].edata["e"].mean(dim=1), rtol=1e-6)           # utils.jl:24-26
+    for aggr, fn in ((operator.add, torch.sum), (max, torch.amax), (min, torch.amin)):
+        assert torch.allclose(gnn.reduce_nodes(aggr, g, x)[:, 3].cpu(), fn(gs[3].ndata["x"], dim=1), rtol=1e-6)
+    r = gnn.softmax_nodes(g, x)
+    assert r.shape == x.shape
+    assert torch.allclose(r[:, :10].cpu(), torch.softmax(gs[0].ndata["x"], dim=1), rtol=1e-5, atol=1e-7)  # utils.jl:30-32
+    r = gnn.softmax_edges(g, e)
+    assert r.shape == e.shape
+    assert torch.allclose(r[:, :60].cpu(), torch.softmax(gs[0].edata["e"], dim=1), rtol=1e-5, atol=1e-6)  # utils.jl:36-38
+    z = gnn.colmajor(torch.rand(4, g.num_graphs).cuda())
+    r = gnn.broadcast_nodes(g, z)
+    assert r.shape == (4, g.num_nodes)
+    assert torch.equal(r[:, 0], z[:, 0]) and torch.equal(r[:, 9], z[:, 0]) and torch.equal(r[:, 10], z[:, 1])   # utils.jl:42-47
+    r = gnn.broadcast_edges(g, z)
+    assert r.shape == (4, g.num_edges)
+    assert torch.equal(r[:, 0], z[:, 0]) and torch.equal(r[:, 59], z[:, 0]) and torch.equal(r[:, 60], z[:, 1])  # utils.jl:51-56
+    # gradients flow through the library's pullbacks
+    xg = x.clone().requires_grad_(True)
+    (gnn.softmax_nodes(g, xg) * gnn.broadcast_nodes(g, gnn.reduce_nodes(max, g, xg))).sum().backward()
+    assert torch.isfinite(xg.grad).all()
+
+    class L:
+        aggr = gnn.mean
+        fgate = staticmethod(lambda v: v[:1])
+        ffeat = staticmethod(lambda v: v)
+    assert gnn.global_pool(L, g, x).shape == (2, 5)
+    u = gnn.global_attention_pool(L, g, x)
+    a = torch.softmax(gs[2].ndata["x"][:1], dim=1)
+    assert torch.allclose(u[:, 2].cpu(), (a * gs[2].ndata["x"]).sum(dim=1), rtol=1e-5)
+
+
+class _NT:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def test_reparameterised_layers(gnn, oracle):
+    rng = np.random.default_rng(1)
+    n, E, Din, Dout = 300, 2000, 16, 8
+    s = rng.integers(1, n + 1, E); t = rng.integers(1, n + 1, E)
+    g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
+    x = rng.standard_normal((n, Din)).astype(np.float32)
+    xt = gnn.unrows(torch.as_tensor(x).cuda())
+    x64 = x.astype(np.float64)
+    dev = lambda a: torch.as_tensor(a.astype(np.float32)).cuda()
+    W1 = rng.standard_normal((Dout, Din)) / 4; W2 = rng.standard_normal((Dout, Din)) / 4; b = rng.standard_normal(Dout)
+    # graph_conv (conv.jl:102-108)
+    l = _NT(weight1=dev(W1), weight2=dev(W2), bias=dev(b), σ=torch.relu, aggr=gnn.mean)
+    m = oracle.propagate_unfused("mean", s, t, n, x64)
+    ref = np.maximum(x64 @ W1.T + m @ W2.T + b, 0)
+    assert rel(gnn.rows(gnn.graph_conv(l, g, xt)).cpu(), ref) < 5e-6
+    # gin_conv (conv.jl:250-256) with nn = identity-ish linear map
+    l = _NT(nn=lambda v: 2.0 * v, ϵ=0.25, aggr=operator.add)
+    ref = 2.0 * (1.25 * x64 + oracle.propagate_unfused("+", s, t, n, x64))
+    assert rel(gnn.rows(gnn.gin_conv(l, g, xt)).cpu(), ref) < 5e-6
+    # sgc_conv (conv.jl:407-448), k = 2, self loops
+    W = rng.standard_normal((Dout, Din)) / 4
+    l = _NT(weight=dev(W), bias=dev(b), k=2, add_self_loops=True, use_edge_weight=False)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    h = x64 @ W.T
+    for _ in range(2):
+        h, _c = oracle.gcn_propagate(s2, t2, n, h)
+    assert rel(gnn.rows(gnn.sgc_conv(l, g, xt)).cpu(), h + b) < 5e-6
+    # agnn_conv (conv.jl:337-352)
+    l = _NT(add_self_loops=True, β=torch.tensor(1.5, device="cuda"))
+    xn = x64 / np.sqrt((x64 ** 2).sum(1, keepdims=True))
+    cos = (xn[t2 - 1] * xn[s2 - 1]).sum(1, keepdims=True)
+    alpha = oracle.softmax_edge_neighbors(t2, n, 1.5 * cos)
+    ref = oracle.scatter("+", alpha * x64[s2 - 1], t2, n)
+    assert rel(gnn.rows(gnn.agnn_conv(l, g, xt)).cpu(), ref) < 1e-5
