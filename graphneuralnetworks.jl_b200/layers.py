@@ -355,15 +355,13 @@ class GATConv(torch.nn.Module):
 # ------------------------------------------------------------------------------------------ SAGEConv
 def sage_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
     """GNNlib/src/layers/conv.jl:277-283: σ.(W * vcat(xi, propagate(copy_xj, g, aggr, xj)) .+ b).
-    W is (out, 2·in): its first `in` columns multiply x_i, the rest the aggregated neighbours, so the vcat
-    temporary is never built."""
+    W is (out, 2·in): its first `in` columns multiply x_i, the rest the aggregated neighbours."""
     check_num_nodes(g, x)
     xj, xi = expand_srcdst(g, x)
     m = propagate(copy_xj, g, l.aggr, xj=xj)
     W = l.weight
-    din = xi.shape[0]
-    out = unrows(torch.addmm(rows(xi) @ W[:, :din].t(), rows(m), W[:, din:].t()))
-    return _sigma(l)(_add_bias(out, _bias(l)))
+    xm = unrows(torch.cat([rows(xi), rows(m)], dim=1))        # vcat(xi, m): (2·in, N)
+    return _linear(l, W, xm, True)                            # σ.(W * vcat(xi, m) .+ b): one GEMM, bias/σ in the epilogue
 
 
 class SAGEConv(torch.nn.Module):
