@@ -394,7 +394,11 @@ def gin_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
     check_num_nodes(g, x)
     xj, xi = expand_srcdst(g, x)
     m = propagate(copy_xj, g, l.aggr, xj=xj)
-    eps = getattr(l, "ϵ", getattr(l, "eps", 0.0))
+    eps = 0.0
+    for name in ("\u03f5", "\u03b5", "eps"):     # ϵ (the reference's field; Python NFKC-normalises it to ε in identifiers)
+        if hasattr(l, name):
+            eps = getattr(l, name)
+            break
     return l.nn((1 + eps) * xi + m)
 
 
