@@ -109,3 +109,23 @@ def test_layer_argument_errors(gnn):
         l(g, x, torch.rand(2))
     with pytest.raises(ValueError):
         l(g, x, conv_weight=torch.zeros(5, 4))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the oracle port of the reference's CPU path) on a tiny bounded sample: one JSON line
+    with the contract's keys; rank != 0 prints nothing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--cpu-nodes", "20000", "--cpu-edges", "100000"]
+    out = subprocess.check_output(cmd, text=True, timeout=300)
+    line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    assert subprocess.check_output(cmd, text=True, timeout=300, env=env).strip() == ""
