@@ -12,8 +12,10 @@ from .graph import (GNNGraph, add_self_loops, batch, colmajor, degree, edge_inde
 from .msgpass import (Fix1, aggregate_neighbors, apply_edges, check_num_edges, check_num_nodes, copy_xi, copy_xj,
                       e_mul_xj, expand_srcdst, mean, propagate, softmax_edge_neighbors, w_mul_xj, xi_dot_xj,
                       xi_sub_xj, xj_sub_xi)
-from .layers import (GATConv, GCNConv, SAGEConv, agnn_conv, gat_conv, gat_message, gcn_conv, gin_conv, graph_conv,
-                     identity, relu, sage_conv, sgc_conv)
+from .layers import (AGNNConv, GATConv, GATv2Conv, GCNConv, GINConv, GatedGraphConv, GraphConv, SAGEConv, SGConv,
+                     TAGConv, TransformerConv, agnn_conv, gat_conv, gat_message, gated_graph_conv, gatv2_conv,
+                     gatv2_message, gcn_conv, gin_conv, graph_conv, identity, relu, sage_conv, sg_conv, sgc_conv,
+                     tag_conv, transformer_conv)
 from .readout import (broadcast_edges, broadcast_nodes, global_attention_pool, global_pool, reduce_edges, reduce_nodes,
                       softmax_edges, softmax_nodes)
 

@@ -11,7 +11,11 @@ bias, σ, negative_slope, channel, heads, concat, add_self_loops, dropout``; SAG
 (GraphNeuralNetworks/src/layers/conv.jl:77-104, 309-346, 770-787).
 
 Arrays are Julia-shaped and column-major: x is (Din, N), weight is (Dout, Din), GAT's ``a`` is (2C, H).
-The dense contractions (W*x) go to cuBLAS sgemm (fp32, no TF32) — a plain library GEMM, as in the reference.
+The dense contractions `σ.(W*x .+ b)` go through gnnb_linear / gnnb_linear_bwd (hand-written tcgen05 3xTF32 kernels with
+the bias/relu epilogue; cuBLASLt for shapes they do not cover) when the shape allows, torch's fp32 matmul otherwise.
+
+Further down: the layers SURVEY.md §8f ranks first because they re-parameterise the same kernels — graph_conv, gin_conv,
+sgc_conv / sg_conv, tag_conv, gated_graph_conv, agnn_conv, gatv2_conv, transformer_conv — with their parameter holders.
 """
 from __future__ import annotations
 
@@ -447,3 +451,367 @@ def agnn_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
     cos_dist = apply_edges(xi_dot_xj, g, xi=xn, xj=xn)
     alpha = softmax_edge_neighbors(g, l.β * cos_dist if hasattr(l, "β") else l.beta * cos_dist)
     return propagate(lambda xi, xj, a: a * xj, g, operator.add, xj=x, e=alpha)
+
+
+def _k_hop_gcn(l, g: GNNGraph, x: torch.Tensor, edge_weight, each_hop: Callable) -> None:
+    """The loop sg_conv and tag_conv share (conv.jl:521-536, 655-682): k rounds of  x <- c' .* A(c' .* x)  with
+    c = 1/sqrt(in-degree); `each_hop(i, x)` sees the features after round i.  Unweighted graphs take the fused GCN
+    kernel (both scalings folded into its load and store)."""
+    use_w = bool(getattr(l, "use_edge_weight", False)) and g.w is not None
+    if edge_weight is None and not use_w:
+        plan = g.plan()
+        xr = _f32(rows(x), plan.device)
+        c = _gcn_c(g)
+        for i in range(int(l.k)):
+            xr = _GCNPropagateFn.apply(xr, plan, c)
+            each_hop(i, unrows(xr))
+        return
+    d = degree(g, torch.float32, dir="in", edge_weight=edge_weight if edge_weight is not None else True)
+    c = (1.0 / torch.sqrt(d)).reshape(1, -1)
+    for i in range(int(l.k)):
+        x = x * c
+        x = (propagate(e_mul_xj, g, operator.add, xj=x, e=edge_weight) if edge_weight is not None
+             else propagate(w_mul_xj, g, operator.add, xj=x))
+        x = x * c
+        each_hop(i, x)
+
+
+def _loops_and_weights(l, g: GNNGraph, edge_weight):
+    if edge_weight is not None:
+        assert edge_weight.numel() == g.num_edges, \
+            f"Wrong number of edge weights (expected {g.num_edges} but given {edge_weight.numel()})"
+    if l.add_self_loops:
+        g = add_self_loops(g)
+        if edge_weight is not None:
+            edge_weight = torch.cat([edge_weight, torch.ones(g.num_nodes, dtype=edge_weight.dtype,
+                                                             device=edge_weight.device)])
+            assert edge_weight.numel() == g.num_edges
+    return g, edge_weight
+
+
+def sg_conv(l, g: GNNGraph, x: torch.Tensor, edge_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:501-543 (SGConv): W applied on the cheaper side of k normalised propagation rounds."""
+    g, edge_weight = _loops_and_weights(l, g, edge_weight)
+    W = l.weight
+    Dout, Din = W.shape
+    if Dout < Din:
+        x = _linear(l, W, x, False)
+    last = [x]
+    _k_hop_gcn(l, g, x, edge_weight, lambda i, h: last.__setitem__(0, h))
+    x = last[0]
+    if Dout >= Din:
+        x = _linear(l, W, x, False)
+    return _add_bias(x, _bias(l))
+
+
+def tag_conv(l, g: GNNGraph, x: torch.Tensor, edge_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:634-686 (TAGConv), as the reference computes it: after round i the running sum
+    S_i = Σ_{j<=i} Â^j x is multiplied by the ONE weight matrix and accumulated:  Σ_i W S_i  (+ bias)."""
+    g, edge_weight = _loops_and_weights(l, g, edge_weight)
+    W = l.weight
+    state = {"pow": None, "total": None}
+
+    def hop(i, h):
+        if i == 0:
+            state["pow"] = h
+            state["total"] = _linear(l, W, h, False)
+        else:
+            state["pow"] = state["pow"] + h
+            state["total"] = state["total"] + _linear(l, W, state["pow"], False)
+
+    _k_hop_gcn(l, g, x, edge_weight, hop)
+    if state["total"] is None:            # k = 0: the reference returns 0 .+ bias
+        b = _bias(l)
+        return torch.zeros((), dtype=x.dtype, device=x.device) if b is None else b.clone()
+    return _add_bias(state["total"], _bias(l))
+
+
+class _GRUCell(torch.nn.Module):
+    """Flux.GRUCell(in => out) on Julia-shaped (D, N) arrays; returns (h', h') like Flux's cell.
+        r = σ(Wi_r x + Wh_r h + b_r);  z = σ(Wi_z x + Wh_z h + b_z);  h~ = tanh(Wi_h x + r .* (Wh_h h) + b_h)
+        h' = (1 - z) .* h~ + z .* h"""
+
+    def __init__(self, ch_in: int, ch_out: int, device=None):
+        super().__init__()
+        self.Wi = torch.nn.Parameter(glorot_uniform(3 * ch_out, ch_in, device=device))
+        self.Wh = torch.nn.Parameter(glorot_uniform(3 * ch_out, ch_out, device=device))
+        self.b = torch.nn.Parameter(torch.zeros(3 * ch_out, device=device))
+        self.ch_out = ch_out
+
+    def forward(self, x, h):
+        o = self.ch_out
+        gx = _matmul(self.Wi, x)
+        gh = _matmul(self.Wh, h)
+        b = self.b.reshape(-1, 1)
+        r = torch.sigmoid(gx[:o] + gh[:o] + b[:o])
+        z = torch.sigmoid(gx[o:2 * o] + gh[o:2 * o] + b[o:2 * o])
+        hc = torch.tanh(gx[2 * o:] + r * gh[2 * o:] + b[2 * o:])
+        hn = (1 - z) * hc + z * h
+        return hn, hn
+
+
+def gated_graph_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:218-233: zero-pad x to `dims`, then num_layers rounds of
+    m = propagate(copy_xj, g, aggr, xj = W_i * h);  h = gru(m, h).   l.weight is (dims, dims, num_layers)."""
+    check_num_nodes(g, x)
+    m_in, n = x.shape
+    assert m_in <= l.dims, "number of input features must be less or equal to output features."
+    if m_in < l.dims:
+        x = unrows(torch.cat([rows(x), torch.zeros(n, l.dims - m_in, dtype=x.dtype, device=x.device)], dim=1))
+    h = x
+    for i in range(int(l.num_layers)):
+        m = _linear(l, l.weight[:, :, i], h, False)
+        m = propagate(copy_xj, g, l.aggr, xj=m)
+        _, h = l.gru(m, h)
+    return h
+
+
+def gatv2_message(l, Wxi, Wxj, e):
+    """GNNlib/src/layers/conv.jl:203-214 (arrays are (C, H, E))."""
+    _, chout = l.channel
+    Wx = Wxi + Wxj
+    if e is not None:
+        Wx = Wx + _jl_reshape3(l.dense_e(e), chout, l.heads)
+    logα = (l.a.unsqueeze(-1) * torch.nn.functional.leaky_relu(Wx, float(l.negative_slope))).sum(dim=0, keepdim=True)
+    return {"logα": logα, "Wxj": Wxj}
+
+
+def _attention_tail(l, out: torch.Tensor) -> torch.Tensor:
+    """`!concat -> mean over heads; reshape(x, :, N); σ.(x .+ bias)` shared by gat_conv and gatv2_conv."""
+    if not l.concat:
+        out = out.mean(dim=1, keepdim=True)
+    out = unrows(rows(out).reshape(out.shape[-1], -1))
+    return _sigma(l)(_add_bias(out, _bias(l)))
+
+
+def gatv2_conv(l, g: GNNGraph, x: torch.Tensor, e: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:171-201.  The logit a·leakyrelu(W_i x_i + W_j x_j) does not split into per-node
+    terms, so the edge part is the reference's composition on the gather / neighbourhood-softmax / scatter kernels."""
+    check_num_nodes(g, x)
+    dense_e = getattr(l, "dense_e", None)
+    assert not (e is None and dense_e is not None), "Input edge features required for this layer"
+    assert not (e is not None and dense_e is None), "Input edge features were not specified in the layer constructor"
+    xj, xi = expand_srcdst(g, x)
+    if l.add_self_loops:
+        assert e is None, "Using edge features and setting add_self_loops=true at the same time is not yet supported."
+        g = add_self_loops(g)
+    _, chout = l.channel
+    Wxi = _jl_reshape3(l.dense_i(xi), chout, l.heads)
+    Wxj = _jl_reshape3(l.dense_j(xj), chout, l.heads)
+    m = apply_edges(Fix1(gatv2_message, l), g, Wxi, Wxj, e)
+    α = softmax_edge_neighbors(g, m["logα"])
+    p = float(getattr(l, "dropout", 0.0) or 0.0)
+    if p > 0:
+        α = torch.nn.functional.dropout(α, p, training=getattr(l, "training", True))
+    out = aggregate_neighbors(g, operator.add, α * m["Wxj"])
+    return _attention_tail(l, out)
+
+
+def transformer_message_uij(l, xi, xj, e):
+    """GNNlib/src/layers/conv.jl:614-621."""
+    key = xj["W4x"]
+    if e["W6e"] is not None:
+        key = key + e["W6e"]
+    return (xi["W3x"] * key).sum(dim=0, keepdim=True) / l.sqrt_out
+
+
+def transformer_message_main(xi, xj, e):
+    """GNNlib/src/layers/conv.jl:623-629."""
+    val = xj["W2x"]
+    if e["W6e"] is not None:
+        val = val + e["W6e"]
+    return e["α"] * val
+
+
+def transformer_conv(l, g: GNNGraph, x: torch.Tensor, e: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GNNlib/src/layers/conv.jl:553-612: multi-head dot-product attention over each in-neighbourhood, then the
+    root-weight / gating / skip / batch-norm / feed-forward tail (dense per-node work, left to torch like Flux's)."""
+    check_num_nodes(g, x)
+    if l.add_self_loops:
+        g = add_self_loops(g)
+    out = l.channels[1]
+    heads = l.heads
+    W1x = l.W1(x) if l.W1 is not None else None
+    W2x = _jl_reshape3(l.W2(x), out, heads)
+    W3x = _jl_reshape3(l.W3(x), out, heads)
+    W4x = _jl_reshape3(l.W4(x), out, heads)
+    W6e = _jl_reshape3(l.W6(e), out, heads) if l.W6 is not None else None
+    m = apply_edges(Fix1(transformer_message_uij, l), g, xi={"W3x": W3x}, xj={"W4x": W4x}, e={"W6e": W6e})
+    α = softmax_edge_neighbors(g, m)
+    h = propagate(transformer_message_main, g, operator.add, xi={"W3x": W3x}, xj={"W2x": W2x}, e={"W6e": W6e, "α": α})
+    if l.concat:
+        h = unrows(rows(h).reshape(h.shape[-1], out * heads))
+    else:
+        h = h.mean(dim=1)                                          # (out, N)
+    if W1x is not None:
+        if l.W5 is not None:
+            β = l.W5(torch.cat([h, W1x, h - W1x], dim=0))
+            h = β * W1x + (1.0 - β) * h
+        else:
+            h = h + W1x
+    if l.skip_connection:
+        assert h.shape[0] == x.shape[0], \
+            "In-channels must correspond to out-channels * heads if skip_connection is used"
+        h = h + x
+    if l.BN1 is not None:
+        h = l.BN1(h)
+    if l.FF is not None:
+        h1 = h
+        h = l.FF(h)
+        if l.skip_connection:
+            h = h + h1
+        if l.BN2 is not None:
+            h = l.BN2(h)
+    return h
+
+
+# ------------------------------------------------------------------ parameter holders for the layers above
+class _DenseAct(_Dense):
+    """Flux.Dense(in => out, σ; bias): `_linear` reads the activation from the `sigma` field."""
+
+    def __init__(self, ch_in, ch_out, sigma: Callable = identity, bias=True, device=None):
+        super().__init__(ch_in, ch_out, bias=bias, device=device)
+        self.sigma = sigma
+
+
+class _BatchNorm(torch.nn.Module):
+    """Flux.BatchNorm(ch) on (ch, N) Julia-shaped arrays (normalises over the node dimension)."""
+
+    def __init__(self, ch, device=None):
+        super().__init__()
+        self.bn = torch.nn.BatchNorm1d(ch, eps=1e-5, momentum=0.1, device=device)
+
+    def forward(self, x):
+        return unrows(self.bn(rows(x)))
+
+
+class GraphConv(torch.nn.Module):
+    """GraphConv(in => out, σ=identity; aggr=+, bias=true) — GraphNeuralNetworks/src/layers/conv.jl:226-251."""
+
+    def __init__(self, ch_in, ch_out, sigma: Callable = identity, *, aggr=operator.add, bias=True, device=None):
+        super().__init__()
+        self.weight1 = torch.nn.Parameter(glorot_uniform(ch_out, ch_in, device=device))
+        self.weight2 = torch.nn.Parameter(glorot_uniform(ch_out, ch_in, device=device))
+        self.bias = torch.nn.Parameter(torch.zeros(ch_out, device=device)) if bias else None
+        self.sigma, self.aggr = sigma, aggr
+
+    def forward(self, g, x):
+        return graph_conv(self, g, x)
+
+
+class GINConv(torch.nn.Module):
+    """GINConv(nn, ϵ; aggr=+) — GraphNeuralNetworks/src/layers/conv.jl:628-640 (ϵ is not trainable there either)."""
+
+    def __init__(self, nn: Callable, eps: float = 0.0, *, aggr=operator.add):
+        super().__init__()
+        self.nn, self.eps, self.aggr = nn, float(eps), aggr
+
+    def forward(self, g, x):
+        return gin_conv(self, g, x)
+
+
+class AGNNConv(torch.nn.Module):
+    """AGNNConv(; init_beta=1, trainable=true, add_self_loops=true) — GraphNeuralNetworks/src/layers/conv.jl:988-1003."""
+
+    def __init__(self, *, init_beta: float = 1.0, trainable: bool = True, add_self_loops: bool = True, device=None):
+        super().__init__()
+        b = torch.tensor([float(init_beta)], device=device)
+        self.beta = torch.nn.Parameter(b) if trainable else b
+        self.add_self_loops = add_self_loops
+
+    def forward(self, g, x):
+        return agnn_conv(self, g, x)
+
+
+class SGConv(torch.nn.Module):
+    """SGConv(in => out, k=1; bias=true, add_self_loops=true, use_edge_weight=false) — conv.jl:1197-1222."""
+
+    def __init__(self, ch_in, ch_out, k: int = 1, *, bias=True, add_self_loops=True, use_edge_weight=False,
+                 device=None):
+        super().__init__()
+        self.weight = torch.nn.Parameter(glorot_uniform(ch_out, ch_in, device=device))
+        self.bias = torch.nn.Parameter(torch.zeros(ch_out, device=device)) if bias else None
+        self.k, self.add_self_loops, self.use_edge_weight = int(k), add_self_loops, use_edge_weight
+
+    def forward(self, g, x, edge_weight=None):
+        return sg_conv(self, g, x, edge_weight)
+
+
+class TAGConv(SGConv):
+    """TAGConv(in => out, k=3; bias=true, add_self_loops=true, use_edge_weight=false) — conv.jl:1265-1286."""
+
+    def __init__(self, ch_in, ch_out, k: int = 3, **kw):
+        super().__init__(ch_in, ch_out, k, **kw)
+
+    def forward(self, g, x, edge_weight=None):
+        return tag_conv(self, g, x, edge_weight)
+
+
+class GatedGraphConv(torch.nn.Module):
+    """GatedGraphConv(out, num_layers; aggr=+) — GraphNeuralNetworks/src/layers/conv.jl:515-530."""
+
+    def __init__(self, dims: int, num_layers: int, *, aggr=operator.add, device=None):
+        super().__init__()
+        w = torch.stack([glorot_uniform(dims, dims, device=device) for _ in range(num_layers)], dim=2)
+        self.weight = torch.nn.Parameter(w)                       # (dims, dims, num_layers)
+        self.gru = _GRUCell(dims, dims, device=device)
+        self.dims, self.num_layers, self.aggr = dims, num_layers, aggr
+
+    def forward(self, g, x):
+        return gated_graph_conv(self, g, x)
+
+
+class GATv2Conv(torch.nn.Module):
+    """GATv2Conv(in => out, σ=identity; heads=1, concat=true, negative_slope=0.2, bias=true, add_self_loops=true,
+    dropout=0) and the (in, ein) => out form — GraphNeuralNetworks/src/layers/conv.jl:413-462."""
+
+    def __init__(self, ch_in, ch_out: int, sigma: Callable = identity, *, heads: int = 1, concat: bool = True,
+                 negative_slope: float = 0.2, bias: bool = True, add_self_loops: bool = True, dropout: float = 0.0,
+                 device=None):
+        super().__init__()
+        cin, ein = ch_in if isinstance(ch_in, tuple) else (ch_in, 0)
+        if add_self_loops:
+            assert ein == 0, "Using edge features and setting add_self_loops=true at the same time is not yet supported."
+        self.dense_i = _Dense(cin, ch_out * heads, bias=bias, device=device)
+        self.dense_j = _Dense(cin, ch_out * heads, bias=False, device=device)
+        self.dense_e = _Dense(ein, ch_out * heads, bias=False, device=device) if ein > 0 else None
+        nb = ch_out * heads if concat else ch_out
+        self.bias = torch.nn.Parameter(torch.zeros(nb, device=device)) if bias else None
+        self.a = torch.nn.Parameter(glorot_uniform(ch_out, heads, device=device))
+        self.sigma, self.negative_slope = sigma, negative_slope
+        self.channel = ((cin, ein), ch_out)
+        self.heads, self.concat, self.add_self_loops, self.dropout = heads, concat, add_self_loops, dropout
+
+    def forward(self, g, x, e=None):
+        return gatv2_conv(self, g, x, e)
+
+
+class TransformerConv(torch.nn.Module):
+    """TransformerConv((in, ein) => out; heads=1, concat=true, add_self_loops=false, bias_qkv=true, bias_root=true,
+    root_weight=true, gating=false, skip_connection=false, batch_norm=false, ff_channels=0)
+    — GraphNeuralNetworks/src/layers/conv.jl:1473-1539."""
+
+    def __init__(self, ch_in, ch_out: int, *, heads: int = 1, concat: bool = True, add_self_loops: bool = False,
+                 bias_qkv: bool = True, bias_root: bool = True, root_weight: bool = True, gating: bool = False,
+                 skip_connection: bool = False, batch_norm: bool = False, ff_channels: int = 0, device=None):
+        super().__init__()
+        cin, ein = ch_in if isinstance(ch_in, tuple) else (ch_in, 0)
+        if add_self_loops:
+            assert ein == 0, "Using edge features and setting add_self_loops=true at the same time is not yet supported."
+        out_mha = ch_out * (heads if concat else 1)
+        self.W1 = _Dense(cin, out_mha, bias=bias_root, device=device) if root_weight else None
+        self.W2 = _Dense(cin, ch_out * heads, bias=bias_qkv, device=device)
+        self.W3 = _Dense(cin, ch_out * heads, bias=bias_qkv, device=device)
+        self.W4 = _Dense(cin, ch_out * heads, bias=bias_qkv, device=device)
+        self.W5 = _DenseAct(3 * out_mha, 1, torch.sigmoid, bias=False, device=device) if gating else None
+        self.W6 = _Dense(ein, ch_out * heads, bias=bias_qkv, device=device) if ein > 0 else None
+        self.FF = (torch.nn.Sequential(_DenseAct(out_mha, ff_channels, relu, device=device),
+                                       _Dense(ff_channels, out_mha, device=device)) if ff_channels > 0 else None)
+        self.BN1 = _BatchNorm(out_mha, device=device) if batch_norm else None
+        self.BN2 = _BatchNorm(out_mha, device=device) if (batch_norm and ff_channels > 0) else None
+        self.channels = ((cin, ein), ch_out)
+        self.heads, self.add_self_loops, self.concat, self.skip_connection = heads, add_self_loops, concat, skip_connection
+        self.sqrt_out = math.sqrt(ch_out)
+
+    def forward(self, g, x, e=None):
+        return transformer_conv(self, g, x, e)

@@ -25,3 +25,13 @@ def oracle():
 def gnn():
     import gnnb200
     return gnnb200
+
+
+@pytest.fixture
+def cpu_abi():
+    """Run the host-side mirror over tests/fake_abi.py (numpy restatement of the C-ABI contract on host memory) for one
+    test.  Host logic only — says nothing about the CUDA kernels."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_abi
+    with fake_abi.installed() as fake:
+        yield fake
