@@ -102,6 +102,9 @@ _SIGS = {
     "gnnb_ipc_open_handle": (_int, [_vp, C.POINTER(_vp)]),
     "gnnb_ipc_close_handle": (_int, [_vp]),
     "gnnb_halo_push": (_int, [_vp, _vp, _vp, _vp, _int, _f32p, _i64, _vp]),
+    "gnnb_sort_edge_index": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
+    "gnnb_coalesce_edges": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "gnnb_graph_csr_device": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_gcn_propagate_host": (_int, [_vp, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_rmat_edges": (_int, [_i64, _i64, C.c_uint64, _vp, _vp, _vp]),

@@ -66,6 +66,14 @@ def unrows(r: torch.Tensor) -> torch.Tensor:
     return r.permute(tuple(range(nd - 1, -1, -1)))
 
 
+def _compute_device(t: torch.Tensor) -> torch.device:
+    """where the library computes for data that lives with `t`: t's GPU, else the current CUDA device (host arrays are
+    staged there; there is no CPU path)."""
+    if t.is_cuda:
+        return t.device
+    return torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+
+
 def _stream(device) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
 
@@ -189,8 +197,7 @@ class GNNGraph:
         if self._plan is not None:
             return self._plan
         if device is None:
-            device = self.s.device if self.s.is_cuda else torch.device("cuda", torch.cuda.current_device()
-                                                                        if torch.cuda.is_available() else 0)
+            device = _compute_device(self.s)
         if _lib.device_count() <= 0:
             raise _lib.GNNBError(_lib.ECUDA, "no CUDA device: the message-passing engine has no CPU fallback")
         h = C.c_void_p()

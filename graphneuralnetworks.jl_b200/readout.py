@@ -17,6 +17,7 @@ import operator
 import torch
 
 from . import _lib
+from . import graph as _graph
 from ._lib import lib
 from .graph import GNNGraph, _Plan, _stream, graph_indicator, rows, unrows
 from .msgpass import _EdgeSoftmaxFn, _GatherFn, _ScatterFn, _aggr_code, _f32
@@ -65,7 +66,7 @@ def reduce_nodes(aggr, g, x: torch.Tensor) -> torch.Tensor:
         assert x.shape[-1] == g.num_nodes
         return _reduce(aggr, _indicator_plan(g, False), x)
     ind = g
-    dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    dev = _graph._compute_device(x)
     return _reduce(aggr, _IndicatorPlan(ind, int(ind.max()), dev), x)
 
 

@@ -241,6 +241,31 @@ int gnnb_ipc_close_handle(void* p);
 int gnnb_halo_push(const int32_t* send_idx_dev, const int64_t* seg_start_host, const void* const* peer_base_host,
                    const int64_t* peer_row0_host, int world, const float* x, int64_t D, void* stream);
 
+/* ------------------------------------------------- edge-list transforms
+ * replaces: sort_edge_index(u, v) (GNNGraphs/src/utils.jl:41-45: sortperm of the zipped pairs, lexicographic and
+ *           stable) — for CuArrays the reference's CUDA extension copies both arrays to the host, sorts there and copies
+ *           back (GNNGraphs/ext/GNNGraphsCUDAExt.jl:24-30).  Here: one 64-bit key per pair, stable device radix sort.
+ * u, v, u_out, v_out: E DEVICE integers of `index_bytes` (4|8) with values in [0, max_index] (0- or 1-based ids alike;
+ * GNNB_EINDEX otherwise); outputs may alias the inputs or be NULL.  perm_out (NULL or E int64, 0-based): sorted
+ * position k holds input pair perm_out[k].  Synchronises the stream. */
+int gnnb_sort_edge_index(const void* u, const void* v, int64_t num_edges, int64_t max_index, int index_bytes,
+                         void* u_out, void* v_out, int64_t* perm_out, void* stream);
+/* replaces: the index half of remove_multi_edges(g; aggr) (GNNGraphs/src/transform.jl:157-190: edge_encoding, sortperm,
+ *           first-occurrence mask, running segment id) and with it to_bidirected (transform.jl:495-510).
+ * src, dst: E DEVICE indices in [index_base, index_base + num_nodes) (GNNB_EINDEX otherwise).  Outputs (DEVICE,
+ * caller-allocated with E entries each): src_out/dst_out — the distinct pairs in (src, dst) order, first *num_unique
+ * entries valid, same width and base as the input; perm_out (int64, 0-based) — the stable sort permutation; seg_out
+ * (int64, 1-based) — which distinct pair sorted edge k collapsed into, i.e. the `idxs` the reference hands to
+ * `_scatter(aggr, w[perm], idxs)`; that scatter is gnnb_scatter on a plan built from (1:E, seg_out).
+ * num_unique is a HOST int64.  Synchronises the stream. */
+int gnnb_coalesce_edges(const void* src, const void* dst, int64_t num_edges, int64_t num_nodes, int index_bytes,
+                        int index_base, void* src_out, void* dst_out, int64_t* perm_out, int64_t* seg_out,
+                        int64_t* num_unique, void* stream);
+/* gnnb_graph_csr with DEVICE destinations (no synchronisation): the COO -> CSR conversion as an API, for callers that
+ * keep working on the device (the reference has no CSR type). */
+int gnnb_graph_csr_device(gnnb_graph_t g, int transposed, int32_t* rowptr_dev, int32_t* col_dev, int32_t* eid_dev,
+                          void* stream);
+
 /* ------------------------------------------------------ host-buffer entries
  * The reference-facing call with HOST arrays (what a CPU-array caller of `propagate` has): copies
  * x (and w) to the device, runs the fused pass, copies `out` back; synchronous.  Used for the

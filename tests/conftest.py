@@ -1,7 +1,9 @@
 import os
 import sys
+from types import SimpleNamespace
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
@@ -35,3 +37,17 @@ def cpu_abi():
     import fake_abi
     with fake_abi.installed() as fake:
         yield fake
+
+
+@pytest.fixture(params=["fake", pytest.param("cuda", marks=pytest.mark.gpu)])
+def be(request):
+    """back end: .dev (where the mirror's tensors live), .calls (entries the fake saw, None on cuda), .tol (scale)"""
+    if request.param == "fake":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import fake_abi
+        with fake_abi.installed() as fake:
+            yield SimpleNamespace(dev=torch.device("cpu"), calls=fake.calls, tol=1.0)
+    else:
+        if not torch.cuda.is_available():
+            pytest.skip("no CUDA device")
+        yield SimpleNamespace(dev=torch.device("cuda"), calls=None, tol=4.0)

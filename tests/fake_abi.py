@@ -320,6 +320,60 @@ class FakeLib:
         _arr(der, (p.ns, H))[...] = _segment(SUM, dz, p.s, p.ns)
         return OK
 
+    # ------------------------------------------------------------------ edge-list transforms
+    def gnnb_sort_edge_index(self, u, v, E, max_index, index_bytes, u_out, v_out, perm_out, stream):
+        self.calls.append("gnnb_sort_edge_index")
+        dt = np.int32 if index_bytes == 4 else np.int64
+        if E == 0:
+            return OK
+        uu, vv = _arr(u, (E,), dt).copy(), _arr(v, (E,), dt).copy()
+        if min(uu.min(), vv.min()) < 0 or max(uu.max(), vv.max()) > max_index:
+            return self._fail(EINDEX, "edge index outside [0, max_index]")
+        perm = np.lexsort((vv, uu))                      # stable, u major
+        if u_out is not None:
+            _arr(u_out, (E,), dt)[...] = uu[perm]
+        if v_out is not None:
+            _arr(v_out, (E,), dt)[...] = vv[perm]
+        if perm_out is not None:
+            _arr(perm_out, (E,), np.int64)[...] = perm
+        return OK
+
+    def gnnb_coalesce_edges(self, src, dst, E, n, index_bytes, index_base, src_out, dst_out, perm_out, seg_out,
+                            num_unique, stream):
+        self.calls.append("gnnb_coalesce_edges")
+        dt = np.int32 if index_bytes == 4 else np.int64
+        _deref(num_unique).value = 0
+        if E == 0:
+            return OK
+        s, t = _arr(src, (E,), dt).astype(np.int64), _arr(dst, (E,), dt).astype(np.int64)
+        if min(s.min(), t.min()) < index_base or max(s.max(), t.max()) >= index_base + n:
+            return self._fail(EINDEX, "edge index out of range")
+        perm = np.lexsort((t, s))
+        ss, ts = s[perm], t[perm]
+        head = np.ones(E, bool)
+        head[1:] = (ss[1:] != ss[:-1]) | (ts[1:] != ts[:-1])
+        seg = np.cumsum(head)
+        nu = int(seg[-1])
+        _arr(src_out, (E,), dt)[:nu] = ss[head]
+        _arr(dst_out, (E,), dt)[:nu] = ts[head]
+        _arr(perm_out, (E,), np.int64)[...] = perm
+        _arr(seg_out, (E,), np.int64)[...] = seg
+        _deref(num_unique).value = nu
+        return OK
+
+    def gnnb_graph_csr_device(self, h, transposed, rowptr, col, eid, stream):
+        self.calls.append("gnnb_graph_csr_device")
+        p = self._p(h)
+        key, other, nrows = (p.t, p.s, p.nd) if not transposed else (p.s, p.t, p.ns)
+        order = np.argsort(key, kind="stable")
+        if rowptr is not None:
+            _arr(rowptr, (nrows + 1,), np.int32)[...] = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=nrows))])
+        if col is not None and p.E:
+            _arr(col, (p.E,), np.int32)[...] = other[order]
+        if eid is not None and p.E:
+            _arr(eid, (p.E,), np.int32)[...] = order
+        return OK
+
     def __getattr__(self, name):
         if name.startswith("gnnb_"):
             raise AttributeError(f"tests/fake_abi.py does not restate {name}; the host logic under test must not need it")
@@ -344,13 +398,13 @@ def installed():
     """Swap the fake ABI in for libgnnb200 in every module of the mirror; restore on exit."""
     import torch
     import gnnb200
-    from gnnb200 import _lib, graph, layers, msgpass, readout
+    from gnnb200 import _lib, graph, layers, msgpass, readout, transform
 
     fake = FakeLib()
-    mods = [_lib, graph, layers, msgpass, readout]
+    mods = [_lib, graph, layers, msgpass, readout, transform]
     saved = [(m, m.lib) for m in mods]
     saved_cuda = (torch.cuda.device, torch.cuda.current_stream)
-    orig_plan = graph.GNNGraph.plan
+    orig_dev = graph._compute_device
     orig_init = graph._Plan.__init__
     made = []                                    # plans holding fake handles: defused before the real library returns
 
@@ -363,14 +417,14 @@ def installed():
             m.lib = fake
         torch.cuda.device = _NullDevice
         torch.cuda.current_stream = lambda device=None: SimpleNamespace(cuda_stream=0)
-        graph.GNNGraph.plan = lambda self, device=None: orig_plan(self, device or torch.device("cpu"))
+        graph._compute_device = lambda t: torch.device("cpu")
         graph._Plan.__init__ = recording_init
         yield fake
     finally:
         for pl in made:
             pl.h = None                          # _Plan.__del__ must never hand a fake handle to gnnb_graph_destroy
         graph._Plan.__init__ = orig_init
-        graph.GNNGraph.plan = orig_plan
+        graph._compute_device = orig_dev
         torch.cuda.device, torch.cuda.current_stream = saved_cuda
         for m, l in saved:
             m.lib = l

@@ -9,9 +9,6 @@ index ops (no code shared with the mirror).  Each test runs on two back ends (fi
   cuda  — `-m gpu`: the same bodies on the real library and kernels.
 """
 import operator
-import os
-import sys
-from types import SimpleNamespace
 
 import numpy as np
 import pytest
@@ -19,20 +16,6 @@ import torch
 
 F64 = torch.float64
 CPU = torch.device("cpu")
-
-
-@pytest.fixture(params=["fake", pytest.param("cuda", marks=pytest.mark.gpu)])
-def be(request):
-    """back end: .dev (where the mirror's tensors live), .calls (entries the fake saw, None on cuda), .tol (scale)"""
-    if request.param == "fake":
-        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-        import fake_abi
-        with fake_abi.installed() as fake:
-            yield SimpleNamespace(dev=CPU, calls=fake.calls, tol=1.0)
-    else:
-        if not torch.cuda.is_available():
-            pytest.skip("no CUDA device")
-        yield SimpleNamespace(dev=torch.device("cuda"), calls=None, tol=4.0)
 
 
 def _c64(a):
