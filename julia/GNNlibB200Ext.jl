@@ -131,6 +131,32 @@ function ChainRulesCore.rrule(::typeof(GNNlib.softmax_edge_neighbors), g::GNNGra
     return α, softmax_pullback
 end
 
+## sort_edge_index on device arrays — replaces GNNGraphs/ext/GNNGraphsCUDAExt.jl:24-30 (copy to the CPU, sort, copy back)
+function GNNGraphs.sort_edge_index(u::CuVector{T}, v::CuVector{T}) where {T <: Union{Int32, Int64}}
+    @assert length(u) == length(v)
+    uo, vo = similar(u), similar(v)
+    isempty(u) && return uo, vo
+    hi = max(maximum(u), maximum(v))
+    check(ccall((:gnnb_sort_edge_index, LIB), Cint,
+                (CuPtr{T}, CuPtr{T}, Int64, Int64, Cint, CuPtr{T}, CuPtr{T}, CuPtr{Int64}, Ptr{Cvoid}),
+                u, v, length(u), hi, sizeof(T), uo, vo, CU_NULL, stream()))
+    return uo, vo
+end
+
+## remove_multi_edges on a device COO graph — the index half of GNNGraphs/src/transform.jl:157-190 in one call; the
+## `_scatter(aggr, ·, idxs)` of the weights / edge features stays the reference's own line (NNlib.scatter on CuArrays).
+function coalesce_edge_index(s::CuVector{T}, t::CuVector{T}, n::Integer) where {T <: Union{Int32, Int64}}
+    E = length(s)
+    so, to = similar(s), similar(t)
+    perm, idxs = CUDA.zeros(Int64, E), CUDA.zeros(Int64, E)
+    nu = Ref{Int64}(0)
+    check(ccall((:gnnb_coalesce_edges, LIB), Cint,
+                (CuPtr{T}, CuPtr{T}, Int64, Int64, Cint, Cint, CuPtr{T}, CuPtr{T}, CuPtr{Int64}, CuPtr{Int64},
+                 Ref{Int64}, Ptr{Cvoid}),
+                s, t, E, n, sizeof(T), 1, so, to, perm, idxs, nu, stream()))
+    return so[1:nu[]], to[1:nu[]], perm .+ 1, idxs          # 1-based permutation, segment id of every sorted edge
+end
+
 # gcn_conv / gat_conv need no new methods: gcn_conv (GNNlib/src/layers/conv.jl:14-72) reaches the fused kernel through
 # the propagate methods above; a further specialisation may call gnnb_gcn_norm + gnnb_gcn_propagate (both 1/sqrt(d)
 # scalings folded into the pass) and gnnb_gat_aggregate(+_bwd) exactly as graphneuralnetworks.jl_b200/layers.py does.

@@ -320,6 +320,31 @@ class FakeLib:
         _arr(der, (p.ns, H))[...] = _segment(SUM, dz, p.s, p.ns)
         return OK
 
+    # ------------------------------------------------------------------ node-partitioned shards
+    def gnnb_gather_rows(self, idx, n, x, D, out, stream):
+        self.calls.append("gnnb_gather_rows")
+        ii = _arr(idx, (n,), np.int32)
+        nrows = int(ii.max()) + 1 if n else 0
+        _arr(out, (n, D))[...] = _arr(x, (nrows, D))[ii]
+        return OK
+
+    def gnnb_propagate_halo(self, h, msg, aggr, x_local, x_halo, n_local, w, cs, ct, D, out, stream):
+        self.calls.append("gnnb_propagate_halo")
+        p = self._p(h)
+        n_halo = p.ns - n_local
+        xv = np.concatenate([_arr(x_local, (n_local, D)), _arr(x_halo, (n_halo, D)) if n_halo else
+                             np.empty((0, D), np.float32)]).astype(np.float64)
+        if cs is not None:
+            xv = xv * _arr(cs, (p.ns,)).astype(np.float64)[:, None]
+        m = xv[p.s]
+        if msg == 1:
+            m = m * _arr(w, (p.E,)).astype(np.float64)[:, None]
+        o = _segment(aggr, m, p.t, p.nd)
+        if ct is not None:
+            o = o * _arr(ct, (p.nd,)).astype(np.float64)[:, None]
+        _arr(out, (p.nd, D))[...] = o
+        return OK
+
     # ------------------------------------------------------------------ edge-list transforms
     def gnnb_sort_edge_index(self, u, v, E, max_index, index_bytes, u_out, v_out, perm_out, stream):
         self.calls.append("gnnb_sort_edge_index")
@@ -398,10 +423,10 @@ def installed():
     """Swap the fake ABI in for libgnnb200 in every module of the mirror; restore on exit."""
     import torch
     import gnnb200
-    from gnnb200 import _lib, graph, layers, msgpass, readout, transform
+    from gnnb200 import _lib, graph, layers, msgpass, partition, readout, transform
 
     fake = FakeLib()
-    mods = [_lib, graph, layers, msgpass, readout, transform]
+    mods = [_lib, graph, layers, msgpass, readout, transform, partition]
     saved = [(m, m.lib) for m in mods]
     saved_cuda = (torch.cuda.device, torch.cuda.current_stream)
     orig_dev = graph._compute_device

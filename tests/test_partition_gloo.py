@@ -114,3 +114,82 @@ def test_balanced_bounds_edge_cases():
     assert b[0] == 0 and b[-1] == 4 and b[1] in (1, 2)
     b = balanced_bounds(torch.ones(3), 8)                         # more ranks than nodes: empty ranges allowed
     assert b[0] == 0 and b[-1] == 3 and all(b[i] <= b[i + 1] for i in range(8))
+
+
+def _worker_layer(rank, world, port, n, E, seed, q):
+    """dist_gcn_conv forward + backward under gloo, the library replaced by the CPU test double (tests/fake_abi.py):
+    the whole host path of the multi-GPU layer — shard plans, c = 1/sqrt(d) with its halo copies, the two halo
+    exchanges, the autograd function, the gradient all-reduce — against the dense full-graph formula."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GNNB_HALO="nccl")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import fake_abi
+    import gnnb200 as gnn
+    from gnnb200 import partition as P
+    rng = np.random.default_rng(seed)
+    s = np.minimum((rng.random(E) ** 3 * n).astype(np.int64), n - 1) + 1
+    t = np.minimum((rng.random(E) ** 2 * n).astype(np.int64), n - 1) + 1
+    Din, Dout = 6, 4
+    x_full = rng.standard_normal((n, Din)).astype(np.float32)
+    dy_full = rng.standard_normal((n, Dout)).astype(np.float32)
+    ok, err = False, ""
+    with fake_abi.installed() as fake:
+        kept, orig = [], P.build_shard
+        P.build_shard = lambda *a, **k: (kept.append(orig(*a, **k)) or kept[-1])
+        dg = P.DistGraph(torch.as_tensor(s), torch.as_tensor(t), n, add_self_loops=True, device="cpu")
+        P.build_shard = orig
+        for sh, d in ((dg.fwd, kept[0]), (dg.bwd, kept[1])):       # what DistGraph._make does on a CUDA device
+            h = C.c_void_p()
+            col, row = d["col"].to(torch.int32).contiguous(), d["row"].to(torch.int32).contiguous()
+            P._lib.check(P.lib.gnnb_graph_create(C.byref(h), col.data_ptr(), row.data_ptr(), row.numel(),
+                                                 d["n_local"] + d["halo"].numel(), d["n_local"], 4, 0, 1, 0))
+            sh.plan = P._Plan(h.value, torch.device("cpu"))
+        torch.manual_seed(0)
+        layer = gnn.GCNConv(Din, Dout, torch.relu)
+        with torch.no_grad():
+            layer.bias.copy_(torch.linspace(-0.5, 0.5, Dout))
+        lo, hi = dg.lo, dg.hi
+        x = gnn.unrows(torch.as_tensor(x_full[lo:hi]).contiguous()).requires_grad_(True)
+        y = P.dist_gcn_conv(layer, dg, x)
+        y.backward(gnn.unrows(torch.as_tensor(dy_full[lo:hi]).contiguous()))
+        dist.all_reduce(layer.weight.grad)
+        dist.all_reduce(layer.bias.grad)
+        # dense reference on the full graph, float64
+        s0, t0 = torch.as_tensor(s) - 1, torch.as_tensor(t) - 1
+        A = torch.zeros(n, n, dtype=torch.float64)
+        A.index_put_((s0, t0), torch.ones(E, dtype=torch.float64), accumulate=True)
+        A += torch.eye(n, dtype=torch.float64)
+        c = 1 / A.sum(0).sqrt()
+        xr = torch.as_tensor(x_full, dtype=torch.float64).requires_grad_(True)
+        W = layer.weight.detach().double().requires_grad_(True)
+        b = layer.bias.detach().double().requires_grad_(True)
+        yr = torch.relu((c[:, None] * (A.t() @ (c[:, None] * xr))) @ W.t() + b)
+        yr.backward(torch.as_tensor(dy_full, dtype=torch.float64))
+        close = lambda a, r: bool(torch.allclose(a.double(), r, rtol=2e-5, atol=2e-6))
+        checks = {"y": close(gnn.rows(y), yr[lo:hi]), "dx": close(gnn.rows(x.grad), xr.grad[lo:hi]),
+                  "dW": close(layer.weight.grad, W.grad), "db": close(layer.bias.grad, b.grad),
+                  "calls": fake.calls.count("gnnb_propagate_halo") == 2 and fake.calls.count("gnnb_gcn_norm") == 1}
+        ok = all(checks.values())
+        err = str(checks)
+    q.put((rank, ok, err))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dist_gcn_conv_gloo_on_the_test_double(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_layer, args=(r, world, port, 50, 400, 5, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
