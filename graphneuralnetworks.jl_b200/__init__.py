@@ -19,5 +19,6 @@ from .layers import (AGNNConv, GATConv, GATv2Conv, GCNConv, GINConv, GatedGraphC
 from .readout import (broadcast_edges, broadcast_nodes, global_attention_pool, global_pool, reduce_edges, reduce_nodes,
                       softmax_edges, softmax_nodes)
 from .transform import csr, remove_multi_edges, remove_self_loops, sort_edge_index, to_bidirected, unbatch
+from .sampling import NeighborLoader, induced_subgraph, sample_edge_ids, sample_neighbors
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -105,6 +105,9 @@ _SIGS = {
     "gnnb_sort_edge_index": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "gnnb_coalesce_edges": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "gnnb_graph_csr_device": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
+    "gnnb_sample_neighbors": (_int, [_vp, _vp, _i64, _int, _int, _i64, _int, _int, C.c_uint64, _vp, _vp, _i64,
+                                     C.POINTER(_i64), _vp]),
+    "gnnb_sample_positions_host": (_int, [_i32, _i64, _int, C.c_uint64, C.c_uint64, _vp, _i64, C.POINTER(_i64)]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_gcn_propagate_host": (_int, [_vp, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_rmat_edges": (_int, [_i64, _i64, C.c_uint64, _vp, _vp, _vp]),

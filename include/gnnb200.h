@@ -266,6 +266,27 @@ int gnnb_coalesce_edges(const void* src, const void* dst, int64_t num_edges, int
 int gnnb_graph_csr_device(gnnb_graph_t g, int transposed, int32_t* rowptr_dev, int32_t* col_dev, int32_t* eid_dev,
                           void* stream);
 
+/* ------------------------------------------------- neighbour sampling
+ * replaces: the edge selection of sample_neighbors(g, nodes, K; dir, replace) (GNNGraphs/src/sampling.jl:68-83), i.e.
+ *           adjacency_list(g, nodes; dir, with_eid = true) — a scan of every edge through a Dict on the CPU
+ *           (GNNGraphs/src/query.jl:176-198) — plus StatsBase.sample(eidlist[i], k; replace) per node.  The plan's CSR
+ *           is that adjacency list, so only the queried rows are touched.
+ * nodes: n_nodes DEVICE ids (index_bytes 4|8, index_base 0|1; GNNB_EINDEX if out of range; repeated ids are sampled
+ *        independently).  dir = GNNB_DIR_IN samples among the in-edges of each node, GNNB_DIR_OUT among the out-edges.
+ * Node j contributes k_j = deg_j (K <= 0), min(K, deg_j) (replace = 0) or K (replace = 1; 0 when deg_j = 0) edges.
+ * offsets_dev (n_nodes + 1 int64): running sums of k_j.  eids_dev (NULL = only count): COO positions (index_base-based)
+ * of the chosen edges, node after node; capacity = entries available (GNNB_ESIZE if too small).  *total_host = Σ k_j.
+ * Draws are counter-based on (seed, j, draw): reproducible per call; without replacement every k-subset of a row is
+ * equally likely.  Synchronises the stream. */
+int gnnb_sample_neighbors(gnnb_graph_t g, const void* nodes, int64_t n_nodes, int index_bytes, int index_base,
+                          int64_t K, int dir, int replace, uint64_t seed, int64_t* offsets_dev, int64_t* eids_dev,
+                          int64_t capacity, int64_t* total_host, void* stream);
+/* The sampler of ONE query, run on the HOST (no GPU needed): the very function the device kernel calls (compiled for
+ * both sides), so that its validity and uniformity can be tested anywhere.  Writes k = k_j positions in [0, deg) to
+ * out (capacity entries available) for the counter (seed, j); *k_out = k. */
+int gnnb_sample_positions_host(int32_t deg, int64_t K, int replace, uint64_t seed, uint64_t j, int64_t* out,
+                               int64_t capacity, int64_t* k_out);
+
 /* ------------------------------------------------------ host-buffer entries
  * The reference-facing call with HOST arrays (what a CPU-array caller of `propagate` has): copies
  * x (and w) to the device, runs the fused pass, copies `out` back; synchronous.  Used for the

@@ -345,6 +345,44 @@ class FakeLib:
         _arr(out, (p.nd, D))[...] = o
         return OK
 
+    # ------------------------------------------------------------------ neighbour sampling
+    def gnnb_sample_neighbors(self, h, nodes, n, index_bytes, index_base, K, d, replace, seed, offsets, eids, capacity,
+                              total, stream):
+        self.calls.append("gnnb_sample_neighbors")
+        p = self._p(h)
+        key, nrows = (p.t, p.nd) if d == DIR_IN else (p.s, p.ns)
+        _deref(total).value = 0
+        off = _arr(offsets, (n + 1,), np.int64)
+        off[0] = 0
+        if n == 0:
+            return OK
+        dt = np.int32 if index_bytes == 4 else np.int64
+        nd = _arr(nodes, (n,), dt).astype(np.int64) - index_base
+        if nd.min() < 0 or nd.max() >= nrows:
+            return self._fail(EINDEX, "node id out of range")
+        order = np.argsort(key, kind="stable")
+        rowptr = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=nrows))])
+        picks = []
+        for j, r in enumerate(nd):
+            row = order[rowptr[r]:rowptr[r + 1]]
+            deg = len(row)
+            k = 0 if deg == 0 else ((K if K > 0 else deg) if replace else (min(K, deg) if K > 0 else deg))
+            rng = np.random.default_rng([int(seed) & 0x7FFFFFFF, j])
+            if k == deg and not replace:
+                picks.append(row)
+            else:
+                picks.append(rng.choice(row, size=k, replace=bool(replace)) if k else row[:0])
+        cnt = np.array([len(x) for x in picks], dtype=np.int64)
+        off[1:] = np.cumsum(cnt)
+        tot = int(off[-1])
+        _deref(total).value = tot
+        if eids is None or tot == 0:
+            return OK
+        if capacity < tot:
+            return self._fail(ESIZE, "eids buffer too small")
+        _arr(eids, (tot,), np.int64)[...] = np.concatenate(picks) + index_base
+        return OK
+
     # ------------------------------------------------------------------ edge-list transforms
     def gnnb_sort_edge_index(self, u, v, E, max_index, index_bytes, u_out, v_out, perm_out, stream):
         self.calls.append("gnnb_sort_edge_index")
@@ -423,10 +461,10 @@ def installed():
     """Swap the fake ABI in for libgnnb200 in every module of the mirror; restore on exit."""
     import torch
     import gnnb200
-    from gnnb200 import _lib, graph, layers, msgpass, partition, readout, transform
+    from gnnb200 import _lib, graph, layers, msgpass, partition, readout, sampling, transform
 
     fake = FakeLib()
-    mods = [_lib, graph, layers, msgpass, readout, transform, partition]
+    mods = [_lib, graph, layers, msgpass, readout, transform, partition, sampling]
     saved = [(m, m.lib) for m in mods]
     saved_cuda = (torch.cuda.device, torch.cuda.current_stream)
     orig_dev = graph._compute_device
