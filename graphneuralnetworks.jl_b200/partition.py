@@ -31,6 +31,13 @@ from . import _lib
 from ._lib import lib
 from .graph import _Plan, _ptr, _stream, rows, unrows
 
+def overlap_enabled() -> bool:
+    """GNNB_OVERLAP=1: run the halo exchange on a side stream under the part of the reduction that only needs local
+    rows (opt-in; sums a row's local and halo contributions separately, so the result is no longer bit-identical to
+    the single-GPU summation order — within the fp32 tolerance instead)."""
+    return os.environ.get("GNNB_OVERLAP", "0") == "1"
+
+
 NODE_COST = 12  # dense per-node work (GEMM, bias, relu, grads) in edge-equivalents, from the 1-GPU profile (1.9 ns/node vs 0.17 ns/edge)
 
 
@@ -93,7 +100,8 @@ def exchange_requests(halo: torch.Tensor, recv_counts: List[int], lo: int, group
 # the distributed graph
 # ---------------------------------------------------------------------------------------------------------
 class _Shard:
-    def __init__(self, d, send_idx, send_counts, plan):
+    def __init__(self, d, send_idx, send_counts, plan, split=None):
+        self.split = split         # (plan over the edges with a local source, plan over the edges with a halo source)
         self.n_local = d["n_local"]
         self.n_halo = int(d["halo"].numel())
         self.recv_counts = d["recv_counts"]
@@ -130,17 +138,30 @@ class DistGraph:
     def _make(self, key0, other0, loops) -> _Shard:
         d = build_shard(key0, other0, self.lo, self.hi, self.bounds, loops)
         send_idx, send_counts = exchange_requests(d["halo"], d["recv_counts"], self.lo, self.group)
-        plan = None
+        plan, split = None, None
         if self.device.type == "cuda":
+            plan, split = self._plans(d)
+        return _Shard(d, send_idx, send_counts, plan, split)
+
+    def _plans(self, d):
+        """the shard's plan over [local | halo] sources and, for the overlapped schedule (GNNB_OVERLAP=1), the same
+        edges split by where the source lives: (local sources -> targets), (halo sources -> targets)."""
+        def make(col, row, n_src):
             h = C.c_void_p()
-            col = d["col"].to(torch.int32).contiguous()
-            row = d["row"].to(torch.int32).contiguous()
+            col, row = col.to(torch.int32).contiguous(), row.to(torch.int32).contiguous()
             with torch.cuda.device(self.device):
-                _lib.check(lib.gnnb_graph_create(C.byref(h), col.data_ptr(), row.data_ptr(), row.numel(),
-                                                 d["n_local"] + d["halo"].numel(), d["n_local"], 4, 0, 1,
-                                                 _stream(self.device)))
-            plan = _Plan(h.value, self.device)
-        return _Shard(d, send_idx, send_counts, plan)
+                _lib.check(lib.gnnb_graph_create(C.byref(h), col.data_ptr(), row.data_ptr(), row.numel(), n_src,
+                                                 d["n_local"], 4, 0, 1, _stream(self.device)))
+            return _Plan(h.value, self.device)
+
+        n_local, n_halo = d["n_local"], int(d["halo"].numel())
+        plan = make(d["col"], d["row"], n_local + n_halo)
+        split = None
+        if overlap_enabled() and self.world > 1:
+            loc = d["col"] < n_local
+            split = (make(d["col"][loc], d["row"][loc], n_local),
+                     make(d["col"][~loc] - n_local, d["row"][~loc], max(n_halo, 1)) if n_halo else None)
+        return plan, split
 
     # -- halo exchange: rows (n_local, D) -> halo rows (n_halo, D)
     def halo(self, shard: _Shard, x_rows: torch.Tensor) -> torch.Tensor:
@@ -247,7 +268,42 @@ class DistGraph:
             self._c = (c, cf.contiguous(), cb.contiguous())
         return self._c
 
+    def _propagate_overlapped(self, shard: _Shard, x_rows: torch.Tensor, cs, ct) -> torch.Tensor:
+        """out = ct .* (A_local (cs_l .* x_local) + A_halo (cs_h .* x_halo)): the exchange runs on a side stream while
+        the main stream reduces the edges whose sources are local; SUM only."""
+        D = x_rows.shape[1]
+        dev = self.device
+        p_loc, p_hal = shard.split
+        n_local = shard.n_local
+        cs_l = None if cs is None else cs[:n_local]
+        cs_h = None if cs is None else cs[n_local:]
+        out = torch.empty_like(x_rows)
+        on_gpu = dev.type == "cuda"
+        if on_gpu:
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(dev)
+            self._side.wait_stream(main)                      # x_rows is complete before the push reads it
+            with torch.cuda.stream(self._side):
+                hptr = self.halo_ptr(shard, x_rows)
+        else:
+            hptr = self.halo_ptr(shard, x_rows)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gnnb_propagate(p_loc.h, 0, _lib.COPY_XJ, _lib.SUM, x_rows.data_ptr(), None, _ptr(cs_l),
+                                          _ptr(ct), D, out.data_ptr(), _stream(dev)))
+        if p_hal is None:
+            return out
+        if on_gpu:
+            main.wait_stream(self._side)                      # every peer's rows have landed
+        part = torch.empty_like(x_rows)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gnnb_propagate(p_hal.h, 0, _lib.COPY_XJ, _lib.SUM, hptr, None, _ptr(cs_h), _ptr(ct), D,
+                                          part.data_ptr(), _stream(dev)))
+        return out.add_(part)
+
     def propagate(self, shard: _Shard, x_rows: torch.Tensor, cs, ct, aggr=_lib.SUM) -> torch.Tensor:
+        if shard.split is not None and aggr == _lib.SUM:
+            return self._propagate_overlapped(shard, x_rows, cs, ct)
         D = x_rows.shape[1]
         hptr = self.halo_ptr(shard, x_rows)
         out = torch.empty_like(x_rows)

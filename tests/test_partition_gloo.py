@@ -116,13 +116,12 @@ def test_balanced_bounds_edge_cases():
     assert b[0] == 0 and b[-1] == 3 and all(b[i] <= b[i + 1] for i in range(8))
 
 
-def _worker_layer(rank, world, port, n, E, seed, q):
+def _worker_layer(rank, world, port, n, E, seed, q, overlap="0"):
     """dist_gcn_conv forward + backward under gloo, the library replaced by the CPU test double (tests/fake_abi.py):
     the whole host path of the multi-GPU layer — shard plans, c = 1/sqrt(d) with its halo copies, the two halo
     exchanges, the autograd function, the gradient all-reduce — against the dense full-graph formula."""
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GNNB_HALO="nccl")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GNNB_HALO="nccl", GNNB_OVERLAP=overlap)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    import ctypes as C
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -143,11 +142,8 @@ def _worker_layer(rank, world, port, n, E, seed, q):
         dg = P.DistGraph(torch.as_tensor(s), torch.as_tensor(t), n, add_self_loops=True, device="cpu")
         P.build_shard = orig
         for sh, d in ((dg.fwd, kept[0]), (dg.bwd, kept[1])):       # what DistGraph._make does on a CUDA device
-            h = C.c_void_p()
-            col, row = d["col"].to(torch.int32).contiguous(), d["row"].to(torch.int32).contiguous()
-            P._lib.check(P.lib.gnnb_graph_create(C.byref(h), col.data_ptr(), row.data_ptr(), row.numel(),
-                                                 d["n_local"] + d["halo"].numel(), d["n_local"], 4, 0, 1, 0))
-            sh.plan = P._Plan(h.value, torch.device("cpu"))
+            sh.plan, sh.split = dg._plans(d)
+        assert (dg.fwd.split is not None) == (overlap == "1")
         torch.manual_seed(0)
         layer = gnn.GCNConv(Din, Dout, torch.relu)
         with torch.no_grad():
@@ -172,7 +168,8 @@ def _worker_layer(rank, world, port, n, E, seed, q):
         close = lambda a, r: bool(torch.allclose(a.double(), r, rtol=2e-5, atol=2e-6))
         checks = {"y": close(gnn.rows(y), yr[lo:hi]), "dx": close(gnn.rows(x.grad), xr.grad[lo:hi]),
                   "dW": close(layer.weight.grad, W.grad), "db": close(layer.bias.grad, b.grad),
-                  "calls": fake.calls.count("gnnb_propagate_halo") == 2 and fake.calls.count("gnnb_gcn_norm") == 1}
+                  "calls": (fake.calls.count("gnnb_propagate_halo") == (0 if overlap == "1" else 2)
+                            and fake.calls.count("gnnb_gcn_norm") == 1)}
         ok = all(checks.values())
         err = str(checks)
     q.put((rank, ok, err))
@@ -180,12 +177,13 @@ def _worker_layer(rank, world, port, n, E, seed, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_dist_gcn_conv_gloo_on_the_test_double(world):
+@pytest.mark.parametrize("world,overlap", [(2, "0"), (3, "0"), (2, "1"), (3, "1")])
+def test_dist_gcn_conv_gloo_on_the_test_double(world, overlap):
+    """overlap = "1": the opt-in schedule that splits every shard into local-source and halo-source edges"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_layer, args=(r, world, port, 50, 400, 5, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker_layer, args=(r, world, port, 50, 400, 5, q, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
