@@ -718,6 +718,7 @@ class AGNNConv(torch.nn.Module):
         b = torch.tensor([float(init_beta)], device=device)
         self.beta = torch.nn.Parameter(b) if trainable else b
         self.add_self_loops = add_self_loops
+        self.trainable = trainable
 
     def forward(self, g, x):
         return agnn_conv(self, g, x)
