@@ -16,6 +16,9 @@ from .layers import (AGNNConv, GATConv, GATv2Conv, GCNConv, GINConv, GatedGraphC
                      TAGConv, TransformerConv, agnn_conv, gat_conv, gat_message, gated_graph_conv, gatv2_conv,
                      gatv2_message, gcn_conv, gin_conv, graph_conv, identity, relu, sage_conv, sg_conv, sgc_conv,
                      tag_conv, transformer_conv)
+from .layers_more import (CGConv, ChebConv, DConv, EdgeConv, EGNNConv, GMMConv, MEGNetConv, NNConv,
+                          ResGatedGraphConv, cg_conv, cheb_conv, d_conv, edge_conv, egnn_conv, gmm_conv, megnet_conv,
+                          nn_conv, res_gated_graph_conv)
 from .readout import (broadcast_edges, broadcast_nodes, global_attention_pool, global_pool, reduce_edges, reduce_nodes,
                       softmax_edges, softmax_nodes)
 from .transform import csr, remove_multi_edges, remove_self_loops, sort_edge_index, to_bidirected, unbatch
