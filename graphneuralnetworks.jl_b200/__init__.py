@@ -23,5 +23,7 @@ from .readout import (broadcast_edges, broadcast_nodes, global_attention_pool, g
                       softmax_edges, softmax_nodes)
 from .transform import csr, remove_multi_edges, remove_self_loops, sort_edge_index, to_bidirected, unbatch
 from .sampling import NeighborLoader, induced_subgraph, sample_edge_ids, sample_neighbors
+from .query import (adjacency_list, adjacency_matrix, has_multi_edges, has_self_loops, inneighbors, is_bidirected,
+                    outneighbors)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -25,7 +25,7 @@ if [ "${1:-}" = "c5" ]; then
     exit 0
 fi
 # 1. the gated CUDA cases of the neighbour sampler (csrc/sample.cu has never run on a GPU)
-GNNB_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_sampling.py tests/test_layers_reference_cases.py tests/test_layers_more.py -q -m gpu -p no:cacheprovider > gpurun_out/sampling_cuda.log 2>&1
+GNNB_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_sampling.py tests/test_layers_reference_cases.py tests/test_layers_more.py tests/test_query.py -q -m gpu -p no:cacheprovider > gpurun_out/sampling_cuda.log 2>&1
 echo "sampling rc=$?"; tail -n 5 gpurun_out/sampling_cuda.log
 # 2. the whole GPU suite on the rebuilt library
 timeout 900 python -m pytest tests -q -m gpu -x -p no:cacheprovider > gpurun_out/pytest_gpu_r2.log 2>&1
