@@ -24,9 +24,9 @@ import numpy as np
 import torch
 
 from .graph import GNNGraph, degree, rows, unrows
-from .layers import (_add_bias, _bias, _Dense, _DenseAct, _jl_reshape3, _linear, _matmul, _sigma, glorot_uniform,
-                     identity, relu)
-from .msgpass import (Fix1, aggregate_neighbors, apply_edges, check_num_edges, check_num_nodes, copy_xj, e_mul_xj,
+from .layers import (_add_bias, _bias, _Dense, _DenseAct, _jl_reshape3, _matmul, _sigma, glorot_uniform, identity,
+                     relu)
+from .msgpass import (Fix1, aggregate_neighbors, apply_edges, check_num_edges, check_num_nodes, e_mul_xj,
                       expand_srcdst, mean, propagate, w_mul_xj, xi_sub_xj)
 
 

@@ -7,7 +7,7 @@
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 

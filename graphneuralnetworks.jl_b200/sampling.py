@@ -16,9 +16,8 @@ sampled neighbourhoods in distribution when frontiers do not overlap, fewer draw
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
-import numpy as np
 import torch
 
 from . import _lib
