@@ -206,3 +206,47 @@ def test_csc_build_and_products(oracle):
     np.testing.assert_allclose(oracle.dense_times_csc(x, csc, transposed=True), (x.T @ A.T).T, rtol=1e-12)
     cu = oracle.csc_build(s, t, n, None, np.float32)      # unweighted: integer counts
     assert (cu[2] == np.round(cu[2])).all() and cu[2].sum() == E
+
+
+# ---- tests/golden/reference_known_answers.json: every transcribed known answer, replayed through the oracle -------
+def test_known_answer_file(oracle):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_known_answers.json")) as f:
+        G = json.load(f)
+    d = G["degree"]
+    for key in ("out", "in", "both"):
+        assert oracle.degree(d["s"], d["t"], d["n"], key).tolist() == d[key], d["source"]
+    np.testing.assert_allclose(oracle.degree(d["s"], d["t"], d["n"], "out", np.asarray(d["w"], np.float32)),
+                               d["out_weighted"], rtol=1e-6)
+    a = G["add_self_loops"]
+    A, A2 = np.asarray(a["A"]), np.asarray(a["A2"])
+    t, s = np.nonzero(A.T)
+    s2, t2 = oracle.add_self_loops(s + 1, t + 1, 4)
+    assert (oracle.dense_adjacency(s2, t2, 4) == A2).all(), a["source"]
+    sm = G["softmax_edge_neighbors"]
+    e = np.random.default_rng(0).standard_normal((4, 3))
+    got = oracle.softmax_edge_neighbors(sm["t"], sm["n"], e)
+    for lo in (0, 2):
+        ex = np.exp(e[lo:lo + 2] - e[lo:lo + 2].max(0))
+        assert rel(got[lo:lo + 2], ex / ex.sum(0)) < 1e-14, sm["source"]
+    c = G["gcn_closed_form"]
+    w = np.asarray(c["w"], dtype=np.float64)
+    y, _ = oracle.gcn_propagate(c["s"], c["t"], c["n"], np.ones((3, 1)), w)
+    dg = oracle.degree(c["s"], c["t"], c["n"], "in", w, dtype=np.float64)
+    assert abs(y[0, 0] - (w[0] / np.sqrt(dg[0] * dg[1]) + w[1] / np.sqrt(dg[0] * dg[2]))) < 1e-12, c["source"]
+    assert abs(y[1, 0] - (w[2] / np.sqrt(dg[1] * dg[0]) + w[3] / np.sqrt(dg[1] * dg[2]))) < 1e-12
+    b = G["to_bidirected"]                                   # remove_multi_edges(mean) of [s;t],[t;s] in (s,t) order
+    s, t = np.asarray(b["s"] + b["t"]), np.asarray(b["t"] + b["s"])
+    enc = (s - 1) * 4 + t
+    perm = np.argsort(enc, kind="stable")
+    head = np.concatenate([[True], enc[perm][1:] > enc[perm][:-1]])
+    seg = np.cumsum(head)
+    assert s[perm][head].tolist() == b["s2"] and t[perm][head].tolist() == b["t2"], b["source"]
+    for key, out in (("w", "w2"), ("e", "e2")):
+        v = np.asarray(b[key] + b[key])[perm]
+        assert oracle.scatter("mean", v[:, None], seg, int(seg[-1]))[:, 0].tolist() == b[out]
+    for name in ("symmetric_graph", "asymmetric_graph"):
+        gr = G[name]
+        A = oracle.dense_adjacency(gr["s"], gr["t"], 4)
+        assert A.astype(int).tolist() == gr.get("adj", gr.get("adj_out")), gr["source"]
