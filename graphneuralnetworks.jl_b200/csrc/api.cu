@@ -94,7 +94,7 @@ int gnnb_device_count(void) {
 }
 int64_t gnnb_launch_count(void) { return g_launches.load(); }
 int gnnb_set_kernel_variant(int v) {
-    if (v < 0 || v > 5) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,5]");
+    if (v < 0 || v > 7) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,7]");
     gnnb::g_variant = v;
     return GNNB_OK;
 }

@@ -22,35 +22,16 @@
 // short row reproduces the reference's fp32 result bit for bit.
 #include "common.cuh"
 #include "segwalk.cuh"
+#include "segparams.cuh"
 #include <math_constants.h>
 #include <math.h>
 
 namespace gnnb {
 
-struct SegParams {
-    const int32_t* __restrict__ rowptr;
-    const int32_t* __restrict__ col;
-    const int32_t* __restrict__ row;
-    const float* __restrict__ x;
-    const float* __restrict__ x2;   // rows of gathered nodes >= split live here (halo buffer); nullptr = single base
-    const float* __restrict__ w;
-    const float* __restrict__ cs;
-    const float* __restrict__ ct;
-    float* __restrict__ out;
-    float* __restrict__ ws;
-    int64_t D;      // features per row (row stride)
-    int32_t E;
-    int32_t nrows;
-    int32_t chunk;
-    int32_t nchunks;
-    int32_t mean;   // divide by the row's edge count at the final store
-    int32_t fill;   // 1: groups write the neutral element into the empty rows they pass over
-    int32_t split;  // first gathered-node id served from x2
-    float sign;     // +1, or -1 to turn MAX into MIN (min(m) = -max(-m))
-};
+// SegParams: segparams.cuh
 
 // kernel variant: 0 = register-staged kernel (default); 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu);
-// 5 = register-staged kernel without the 64-register cap
+// 5 = register-staged kernel without the 64-register cap; 6, 7 = index-prefetch kernel (segprefetch.cu)
 int g_variant = 0;
 
 template <int VEC> struct VecT;
@@ -259,6 +240,8 @@ __global__ void fill_empty_rows_kernel(const int32_t* __restrict__ rowptr, float
     if (rowptr[r] == rowptr[r + 1]) out[i] = v;
 }
 
+int launch_seg_prefetch(const SegParams& p, bool ismax, int loads, dim3 grid, cudaStream_t st);   // segprefetch.cu
+
 template <int VEC, int TPR, int K, bool ISMAX>
 static int launch_seg(const SegParams& p, cudaStream_t st) {
     const int gpb = 256 / TPR;  // groups per block
@@ -266,6 +249,8 @@ static int launch_seg(const SegParams& p, cudaStream_t st) {
     // One warp per 512 B row (D = 128 fp32): throughput follows the number of resident warps, not the loads per warp
     // (profiles/r1_seg_variants.md): cap the kernel at 64 registers => 4 CTAs x 8 warps per SM.  Variant 5 keeps the
     // uncapped build (77 registers, 24 warps) for A/B runs.
+    if (VEC == 4 && TPR == 32 && K == 1 && (g_variant == 6 || g_variant == 7))
+        return launch_seg_prefetch(p, ISMAX, g_variant == 6 ? 8 : 6, grid, st);
     if (VEC == 4 && TPR == 32 && K == 1 && g_variant != 5) {
         seg_reduce_kernel<4, 32, 1, ISMAX, 8, 4><<<grid, 256, 0, st>>>(p);
         GNNB_LAUNCHED();

@@ -310,7 +310,9 @@ int gnnb_set_chunk_edges(int chunk);
 /* A/B switch for the fused segmented reduce on fp32 rows of 128/256/512 floats (results are bit-identical):
  * 0 = register-staged LDG.128 kernel, capped at 64 registers for 32 resident warps/SM (default, fastest measured);
  * 1 = TMA-staged: one cp.async.bulk (UBLKCP) per row into a shared-memory ring, mbarrier completion;
- * 2..4 = cp.async (LDGSTS) rings of 64/32/16 rows per warp;  5 = register-staged kernel without the register cap.
+ * 2..4 = cp.async (LDGSTS) rings of 64/32/16 rows per warp;  5 = register-staged kernel without the register cap;
+ * 6, 7 = the default kernel with the next group's index words (col, row, cs[col], w) prefetched under the current
+ * group's row loads, 8 / 6 row loads in flight (written after round 1's GPU budget: unmeasured).
  * Measurements: profiles/r1_seg_variants.md. */
 int gnnb_set_kernel_variant(int v);
 
