@@ -94,7 +94,7 @@ int gnnb_device_count(void) {
 }
 int64_t gnnb_launch_count(void) { return g_launches.load(); }
 int gnnb_set_kernel_variant(int v) {
-    if (v < 0 || v > 7) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,7]");
+    if (v < 0 || v > 9) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,9]");
     gnnb::g_variant = v;
     return GNNB_OK;
 }

@@ -56,6 +56,7 @@ struct Csr {
     int32_t nrows = 0;  // reduction rows (targets; sources when transposed)
     int32_t ncols = 0;  // gathered nodes
     float* invdeg = nullptr;  // lazily: 1/max(deg,1) per row (for MEAN)
+    int32_t* chunk_info = nullptr;  // lazily (kernel variants 8, 9): 4 ints per chunk = chunk_bounds() precomputed
     bool built = false;
 };
 

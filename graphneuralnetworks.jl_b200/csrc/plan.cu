@@ -92,7 +92,7 @@ __global__ void selfloop_rows_kernel(const int32_t* __restrict__ rowptr, int32_t
 // ---- helpers ------------------------------------------------------------------------------------
 static void free_csr(Csr& c) {
     cudaFree(c.rowptr); cudaFree(c.col); cudaFree(c.row); cudaFree(c.eid);
-    cudaFree(c.long_rows); cudaFree(c.invdeg);
+    cudaFree(c.long_rows); cudaFree(c.invdeg); cudaFree(c.chunk_info);
     c = Csr();
 }
 

@@ -1,11 +1,13 @@
-// segprefetch.cu — A/B variants 6 and 7 of the fused segmented reduce for rows of 128 floats (one warp = one 512 B row).
+// segprefetch.cu — A/B variants 6..9 of the fused segmented reduce for rows of 128 floats (one warp = one 512 B row).
 //
 // Same decomposition, same arithmetic in the same order as seg_reduce_kernel<4,32,1,·> (segreduce.cu) — results are
 // bit-identical — with one change to the schedule: the per-edge index words of the NEXT group of 32 edges (col, row,
 // cs[col], w) are requested before the current group's rows are reduced.  In the default kernel a warp starts every
 // group with two dependent global loads (col, then cs[col]) during which it has no row load in flight; with 32 resident
 // warps per SM and a kernel whose throughput follows the number of requests in flight (profiles/r1_seg_variants.md),
-// those bubbles are about a fifth of a warp's time per chunk.  Kept in its own translation unit so that the measured
+// those bubbles are about a fifth of a warp's time per chunk.  Variants 8, 9 additionally read the chunk decomposition
+// (chunk_bounds) from a 16 B-per-chunk table built once per plan instead of recomputing it through three dependent
+// loads in every warp's prologue.  Kept in its own translation unit so that the measured
 // default kernels keep their exact code.  Written after round 1's GPU budget was spent: not yet measured
 // (scripts/sweep_variants.py VARIANTS=0,6,7 checks bit-identity and times it).
 #include "common.cuh"
@@ -40,8 +42,21 @@ __device__ __forceinline__ float4 pf_finish(float4 acc, const SegParams& p, int 
     return acc;
 }
 
+// flags of a precomputed chunk record
+constexpr int CI_HEAD = 1, CI_TAIL = 2;
+
+// chunk_bounds() of every chunk, once per plan: the kernel prologue becomes one 16 B load instead of a chain of three
+// dependent ones (row[a] -> rowptr[r0], rowptr[r0+1]; row[z-1] -> rowptr[r1] ...)
+__global__ void chunk_info_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ row, int C, int E,
+                                  int nchunks, int4* __restrict__ info) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nchunks) return;
+    const ChunkBounds b = chunk_bounds(rowptr, row, k, C, E, nchunks);
+    info[k] = make_int4(b.e_begin, b.e_end, b.prev_row, (b.head_partial ? CI_HEAD : 0) | (b.tail_partial ? CI_TAIL : 0));
+}
+
 template <bool ISMAX, int U>
-__global__ void __launch_bounds__(256, 4) seg_reduce_prefetch_kernel(const SegParams p) {
+__global__ void __launch_bounds__(256, 4) seg_reduce_prefetch_kernel(const SegParams p, const int32_t* __restrict__ chunk_info) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int TPR = 32;
     const int lig = threadIdx.x % TPR;
@@ -51,9 +66,20 @@ __global__ void __launch_bounds__(256, 4) seg_reduce_prefetch_kernel(const SegPa
     const float neutral = ISMAX ? -CUDART_INF_F : 0.f;
     const float fillv = ISMAX ? (p.sign < 0.f ? CUDART_INF_F : -CUDART_INF_F) : 0.f;
 
-    const ChunkBounds cb = chunk_bounds(p.rowptr, p.row, k, p.chunk, p.E, p.nchunks);
-    const int e_begin = cb.e_begin, e_end = cb.e_end, prev_row = cb.prev_row;
-    const bool head_partial = cb.head_partial, tail_partial = cb.tail_partial;
+    int e_begin = 0, e_end = 0, prev_row = -1;
+    bool head_partial = false, tail_partial = false;
+    if (chunk_info != nullptr) {
+        if (k < p.nchunks) {
+            const int4 ci = __ldg(reinterpret_cast<const int4*>(chunk_info) + k);
+            e_begin = ci.x; e_end = ci.y; prev_row = ci.z;
+            head_partial = (ci.w & CI_HEAD) != 0;
+            tail_partial = (ci.w & CI_TAIL) != 0;
+        }
+    } else {
+        const ChunkBounds cb = chunk_bounds(p.rowptr, p.row, k, p.chunk, p.E, p.nchunks);
+        e_begin = cb.e_begin; e_end = cb.e_end; prev_row = cb.prev_row;
+        head_partial = cb.head_partial; tail_partial = cb.tail_partial;
+    }
 
     float4 acc = make_float4(neutral, neutral, neutral, neutral);
     int r = -1;
@@ -144,13 +170,32 @@ __global__ void __launch_bounds__(256, 4) seg_reduce_prefetch_kernel(const SegPa
 
 }  // namespace
 
-int launch_seg_prefetch(const SegParams& p, bool ismax, int loads, dim3 grid, cudaStream_t st) {
+// variants 8, 9: build (once per plan and direction) and attach the precomputed chunk records
+int ensure_chunk_info(gnnb_graph* g, const Csr& c, const int32_t** out, cudaStream_t st) {
+    Csr& mc = const_cast<Csr&>(c);          // c is g->by_dst or g->by_src, both owned (mutably) by the plan
+    const int32_t nchunks = (int32_t)ceil_div(g->E, g->chunk);
+    if (mc.chunk_info == nullptr && nchunks > 0) {
+        std::lock_guard<std::mutex> lock(g->mu);
+        if (mc.chunk_info == nullptr) {
+            int32_t* buf = nullptr;
+            GNNB_CUDA(cudaMalloc(&buf, sizeof(int4) * (size_t)nchunks));
+            chunk_info_kernel<<<(unsigned)ceil_div(nchunks, 256), 256, 0, st>>>(c.rowptr, c.row, g->chunk, (int)g->E, nchunks,
+                                                                             reinterpret_cast<int4*>(buf));
+            GNNB_LAUNCHED();
+            mc.chunk_info = buf;
+        }
+    }
+    *out = mc.chunk_info;
+    return GNNB_OK;
+}
+
+int launch_seg_prefetch(const SegParams& p, const int32_t* chunk_info, bool ismax, int loads, dim3 grid, cudaStream_t st) {
     if (loads == 8) {
-        if (ismax) seg_reduce_prefetch_kernel<true, 8><<<grid, 256, 0, st>>>(p);
-        else seg_reduce_prefetch_kernel<false, 8><<<grid, 256, 0, st>>>(p);
+        if (ismax) seg_reduce_prefetch_kernel<true, 8><<<grid, 256, 0, st>>>(p, chunk_info);
+        else seg_reduce_prefetch_kernel<false, 8><<<grid, 256, 0, st>>>(p, chunk_info);
     } else {
-        if (ismax) seg_reduce_prefetch_kernel<true, 6><<<grid, 256, 0, st>>>(p);
-        else seg_reduce_prefetch_kernel<false, 6><<<grid, 256, 0, st>>>(p);
+        if (ismax) seg_reduce_prefetch_kernel<true, 6><<<grid, 256, 0, st>>>(p, chunk_info);
+        else seg_reduce_prefetch_kernel<false, 6><<<grid, 256, 0, st>>>(p, chunk_info);
     }
     GNNB_LAUNCHED();
     return GNNB_OK;

@@ -31,7 +31,7 @@ namespace gnnb {
 // SegParams: segparams.cuh
 
 // kernel variant: 0 = register-staged kernel (default); 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu);
-// 5 = register-staged kernel without the 64-register cap; 6, 7 = index-prefetch kernel (segprefetch.cu)
+// 5 = register-staged kernel without the 64-register cap; 6, 7 = index-prefetch kernel (segprefetch.cu); 8, 9 = the same reading chunk bounds precomputed in the plan
 int g_variant = 0;
 
 template <int VEC> struct VecT;
@@ -240,7 +240,11 @@ __global__ void fill_empty_rows_kernel(const int32_t* __restrict__ rowptr, float
     if (rowptr[r] == rowptr[r + 1]) out[i] = v;
 }
 
-int launch_seg_prefetch(const SegParams& p, bool ismax, int loads, dim3 grid, cudaStream_t st);   // segprefetch.cu
+// segprefetch.cu (A/B variants 6..9); the chunk table travels beside SegParams so that the struct — and with it the
+// code of every measured kernel — stays exactly as it was
+int launch_seg_prefetch(const SegParams& p, const int32_t* chunk_info, bool ismax, int loads, dim3 grid, cudaStream_t st);
+int ensure_chunk_info(gnnb_graph* g, const Csr& c, const int32_t** out, cudaStream_t st);
+static thread_local const int32_t* g_chunk_info = nullptr;   // set by seg_reduce() for the launch that follows
 
 template <int VEC, int TPR, int K, bool ISMAX>
 static int launch_seg(const SegParams& p, cudaStream_t st) {
@@ -249,8 +253,8 @@ static int launch_seg(const SegParams& p, cudaStream_t st) {
     // One warp per 512 B row (D = 128 fp32): throughput follows the number of resident warps, not the loads per warp
     // (profiles/r1_seg_variants.md): cap the kernel at 64 registers => 4 CTAs x 8 warps per SM.  Variant 5 keeps the
     // uncapped build (77 registers, 24 warps) for A/B runs.
-    if (VEC == 4 && TPR == 32 && K == 1 && (g_variant == 6 || g_variant == 7))
-        return launch_seg_prefetch(p, ISMAX, g_variant == 6 ? 8 : 6, grid, st);
+    if (VEC == 4 && TPR == 32 && K == 1 && g_variant >= 6 && g_variant <= 9)
+        return launch_seg_prefetch(p, g_chunk_info, ISMAX, (g_variant & 1) ? 6 : 8, grid, st);
     if (VEC == 4 && TPR == 32 && K == 1 && g_variant != 5) {
         seg_reduce_kernel<4, 32, 1, ISMAX, 8, 4><<<grid, 256, 0, st>>>(p);
         GNNB_LAUNCHED();
@@ -306,6 +310,8 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
         fill_empty_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(c.rowptr, a.out, c.nrows, a.D, v);
         GNNB_LAUNCHED();
     }
+    g_chunk_info = nullptr;
+    if (g_variant == 8 || g_variant == 9) GNNB_TRY(ensure_chunk_info(g, c, &g_chunk_info, st));   // segprefetch.cu
     p.ws = nullptr;
     if (c.n_long > 0) {
         GNNB_TRY(ensure_ws(g, (size_t)2 * p.nchunks * a.D * sizeof(float)));

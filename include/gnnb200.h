@@ -312,7 +312,9 @@ int gnnb_set_chunk_edges(int chunk);
  * 1 = TMA-staged: one cp.async.bulk (UBLKCP) per row into a shared-memory ring, mbarrier completion;
  * 2..4 = cp.async (LDGSTS) rings of 64/32/16 rows per warp;  5 = register-staged kernel without the register cap;
  * 6, 7 = the default kernel with the next group's index words (col, row, cs[col], w) prefetched under the current
- * group's row loads, 8 / 6 row loads in flight (written after round 1's GPU budget: unmeasured).
+ * group's row loads, 8 / 6 row loads in flight;  8, 9 = the same, reading the chunk decomposition from a 16 B-per-chunk
+ * table built once per plan instead of three dependent loads per warp (6..9 were written after round 1's GPU budget:
+ * unmeasured; they live in their own translation unit and leave the code of variants 0..5 untouched).
  * Measurements: profiles/r1_seg_variants.md. */
 int gnnb_set_kernel_variant(int v);
 

@@ -34,7 +34,7 @@ echo "pytest -m gpu rc=$?"; tail -n 3 gpurun_out/pytest_gpu_r2.log
 timeout 300 python scripts/time_transforms.py > gpurun_out/time_transforms.log 2>&1
 echo "time_transforms rc=$?"; cat gpurun_out/time_transforms.log
 # 4. A/B of the index-prefetch variants of the fused kernel (bit-identity is checked by the sweep itself)
-VARIANTS=0,6,7,0 timeout 600 python scripts/sweep_variants.py > gpurun_out/sweep_prefetch.log 2>&1
+VARIANTS=0,6,7,8,9,0 timeout 900 python scripts/sweep_variants.py > gpurun_out/sweep_prefetch.log 2>&1
 echo "sweep rc=$?"; cat gpurun_out/sweep_prefetch.log
 # 5. one ncu capture of every kernel family (about 40 replays each at N = 2 M, E = 20 M), summarised into profiles/
 timeout 1500 ncu --set full --clock-control none --import-source on -f -o gpurun_out/all_kernels \

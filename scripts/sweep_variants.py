@@ -16,7 +16,7 @@ x = torch.randn(n, D, device=dev)
 out = torch.empty_like(x)
 res = []
 CHUNKS = [int(c) for c in os.environ.get('CHUNKS', '128').split(',')]
-VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '0,5,6,7').split(',')]
+VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '0,5,6,7,8,9').split(',')]
 for chunk in CHUNKS:
     gnn._lib.check(lib.gnnb_set_chunk_edges(chunk))
     g = gnn.rmat_graph(n, E, 17, device=dev)
