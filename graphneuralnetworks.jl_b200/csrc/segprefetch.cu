@@ -1,8 +1,8 @@
 // segprefetch.cu — A/B variants 6..9 of the fused segmented reduce for rows of 128 floats (one warp = one 512 B row).
 //
 // Same decomposition, same arithmetic in the same order as seg_reduce_kernel<4,32,1,·> (segreduce.cu) — results are
-// bit-identical — with one change to the schedule: the per-edge index words of the NEXT group of 32 edges (col, row,
-// cs[col], w) are requested before the current group's rows are reduced.  In the default kernel a warp starts every
+// bit-identical — with one change to the schedule: the per-edge index words of the NEXT group of 32 edges are requested
+// around the current group's row reduction (col, row, w before it; the dependent cs[col] after it).  In the default kernel a warp starts every
 // group with two dependent global loads (col, then cs[col]) during which it has no row load in flight; with 32 resident
 // warps per SM and a kernel whose throughput follows the number of requests in flight (profiles/r1_seg_variants.md),
 // those bubbles are about a fifth of a warp's time per chunk.  Variants 8, 9 additionally read the chunk decomposition
@@ -106,27 +106,33 @@ __global__ void __launch_bounds__(256, 4) seg_reduce_prefetch_kernel(const SegPa
         for (int q = lo + 1; q < hi; ++q)
             if (fact) *reinterpret_cast<float4*>(p.out + (size_t)q * p.D + foff) = make_float4(fillv, fillv, fillv, fillv);
     };
-    // index words of the group of 32 edges starting at e0, one edge per lane
-    auto load_idx = [&](int e0, int& c, int& d, float& s1, float& s2) {
+    // Index words of the group of 32 edges starting at e0, one edge per lane, in two phases because a warp issues in
+    // order: phase A (col, row, w) has no dependency and is requested BEFORE the current group's rows are reduced;
+    // phase B (cs[col]) needs col and is requested AFTER them, when col has long arrived — requested any earlier it would
+    // park the warp for a full memory latency with no row load in flight, which is exactly the bubble to remove.
+    auto load_a = [&](int e0, int& c, int& d, float& s2) {
         const int pe = e0 + lig;
-        c = 0; d = -1; s1 = 1.f; s2 = 1.f;
+        c = 0; d = -1; s2 = 1.f;
         if (pe < e_end) {
             c = __ldg(p.col + pe);
             d = __ldg(p.row + pe);
-            if (p.cs) s1 = __ldg(p.cs + c);
             if (p.w) s2 = __ldg(p.w + pe);
             if (p.sign < 0.f) s2 = -s2;
         }
+    };
+    auto load_b = [&](int e0, int c) -> float {
+        return (p.cs != nullptr && e0 + lig < e_end) ? __ldg(p.cs + c) : 1.f;
     };
 
     int e = e_begin;
     int c_n, d_n;
     float s1_n, s2_n;
-    load_idx(e, c_n, d_n, s1_n, s2_n);
+    load_a(e, c_n, d_n, s2_n);
+    s1_n = load_b(e, c_n);
     while (__any_sync(FULL, e < e_end)) {
         const int c_l = c_n, d_l = d_n;
         const float s1_l = s1_n, s2_l = s2_n;
-        load_idx(e + TPR, c_n, d_n, s1_n, s2_n);              // in flight while this group's rows are reduced
+        load_a(e + TPR, c_n, d_n, s2_n);                      // in flight while this group's rows are reduced
         const int nb = e_end - e;
 #pragma unroll 1
         for (int j0 = 0; j0 < TPR; j0 += U) {
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(256, 4) seg_reduce_prefetch_kernel(const SegPa
                 }
             }
         }
+        s1_n = load_b(e + TPR, c_n);                          // col of the next group is here by now: no stall
         e += TPR;
     }
     if (e_begin < e_end) {
