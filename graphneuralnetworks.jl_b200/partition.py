@@ -302,6 +302,20 @@ class DistGraph:
         return out.add_(part)
 
     def propagate(self, shard: _Shard, x_rows: torch.Tensor, cs, ct, aggr=_lib.SUM) -> torch.Tensor:
+        slices = int(os.environ.get("GNNB_HALO_SLICES", "1"))
+        if slices > 1 and x_rows.shape[1] % slices == 0 and not getattr(self, "_slicing", False):
+            # column-sliced pass: exchange and reduce `D / slices` feature columns at a time, so that the halo buffers
+            # shrink by `slices` (config 5: 62 GB of halo rows per pass at D = 256 do not fit beside the features);
+            # costs two strided copies of the local rows and re-reads the index arrays once per slice
+            w = x_rows.shape[1] // slices
+            out = torch.empty_like(x_rows)
+            self._slicing = True
+            try:
+                for i in range(slices):
+                    out[:, i * w:(i + 1) * w] = self.propagate(shard, x_rows[:, i * w:(i + 1) * w].contiguous(), cs, ct, aggr)
+            finally:
+                self._slicing = False
+            return out
         if shard.split is not None and aggr == _lib.SUM:
             return self._propagate_overlapped(shard, x_rows, cs, ct)
         D = x_rows.shape[1]

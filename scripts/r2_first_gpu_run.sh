@@ -19,7 +19,7 @@ if [ "${1:-}" = "dist" ]; then
 fi
 if [ "${1:-}" = "c5" ]; then
     # never run in round 1: every rank generates the 1 B-edge RMAT list (16 GB) and keeps its shard
-    timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 \
+    GNNB_HALO_SLICES=4 timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 \
         bench.py --gpus 8 --nodes 100000000 --edges 1000000000 --dim 256 --steps 5 --warmup 3 --no-e2e > gpurun_out/bench_c5.log 2>&1
     echo "c5 rc=$?"; tail -n 2 gpurun_out/bench_c5.log | cut -c1-600
     exit 0

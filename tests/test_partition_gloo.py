@@ -116,11 +116,11 @@ def test_balanced_bounds_edge_cases():
     assert b[0] == 0 and b[-1] == 3 and all(b[i] <= b[i + 1] for i in range(8))
 
 
-def _worker_layer(rank, world, port, n, E, seed, q, overlap="0"):
+def _worker_layer(rank, world, port, n, E, seed, q, overlap="0", slices="1"):
     """dist_gcn_conv forward + backward under gloo, the library replaced by the CPU test double (tests/fake_abi.py):
     the whole host path of the multi-GPU layer — shard plans, c = 1/sqrt(d) with its halo copies, the two halo
     exchanges, the autograd function, the gradient all-reduce — against the dense full-graph formula."""
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GNNB_HALO="nccl", GNNB_OVERLAP=overlap)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GNNB_HALO="nccl", GNNB_OVERLAP=overlap, GNNB_HALO_SLICES=slices)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -168,7 +168,7 @@ def _worker_layer(rank, world, port, n, E, seed, q, overlap="0"):
         close = lambda a, r: bool(torch.allclose(a.double(), r, rtol=2e-5, atol=2e-6))
         checks = {"y": close(gnn.rows(y), yr[lo:hi]), "dx": close(gnn.rows(x.grad), xr.grad[lo:hi]),
                   "dW": close(layer.weight.grad, W.grad), "db": close(layer.bias.grad, b.grad),
-                  "calls": (fake.calls.count("gnnb_propagate_halo") == (0 if overlap == "1" else 2)
+                  "calls": (fake.calls.count("gnnb_propagate_halo") == (0 if overlap == "1" else 2 * int(slices))
                             and fake.calls.count("gnnb_gcn_norm") == 1)}
         ok = all(checks.values())
         err = str(checks)
@@ -177,13 +177,16 @@ def _worker_layer(rank, world, port, n, E, seed, q, overlap="0"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,overlap", [(2, "0"), (3, "0"), (2, "1"), (3, "1")])
-def test_dist_gcn_conv_gloo_on_the_test_double(world, overlap):
-    """overlap = "1": the opt-in schedule that splits every shard into local-source and halo-source edges"""
+@pytest.mark.parametrize("world,overlap,slices", [(2, "0", "1"), (3, "0", "1"), (2, "1", "1"), (3, "1", "1"),
+                                                  (2, "0", "2"), (2, "1", "2")])
+def test_dist_gcn_conv_gloo_on_the_test_double(world, overlap, slices):
+    """overlap = "1": the opt-in schedule that splits every shard into local-source and halo-source edges;
+    slices = "2": the opt-in column-sliced exchange (GNNB_HALO_SLICES)"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_layer, args=(r, world, port, 50, 400, 5, q, overlap)) for r in range(world)]
+    procs = [ctx.Process(target=_worker_layer, args=(r, world, port, 50, 400, 5, q, overlap, slices))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
