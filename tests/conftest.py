@@ -51,12 +51,3 @@ def be(request):
         if not torch.cuda.is_available():
             pytest.skip("no CUDA device")
         yield SimpleNamespace(dev=torch.device("cuda"), calls=None, tol=4.0)
-
-
-@pytest.fixture
-def be_unvalidated(be):
-    """`be` for tests whose CUDA variant was written after the round's GPU budget was spent: the fake back end always
-    runs, the cuda back end only with GNNB_RUN_UNVALIDATED=1 (scripts/r2_first_gpu_run.sh) until it has passed once."""
-    if be.dev.type == "cuda" and os.environ.get("GNNB_RUN_UNVALIDATED") != "1":
-        pytest.skip("CUDA variant not yet run on a GPU (set GNNB_RUN_UNVALIDATED=1)")
-    return be

@@ -1,7 +1,6 @@
 """The remaining functional layers (graphneuralnetworks.jl_b200/layers_more.py: cheb, edge, nn, res-gated, cg, megnet,
 gmm, egnn, d conv) against float64 formulas written with dense adjacency matrices / explicit per-edge loops — no code
-shared with the mirror.  Forward and input gradients.  Back ends: the CPU test double always; the CUDA variants are new
-and stay skipped until they have run once (GNNB_RUN_UNVALIDATED=1)."""
+shared with the mirror.  Forward and input gradients.  Back ends: the CPU test double and (under -m gpu) CUDA."""
 import operator
 
 import numpy as np
@@ -79,8 +78,8 @@ def randomise_biases(rng, module):
 
 
 @pytest.mark.parametrize("k,weights", [(2, False), (4, False), (3, True)])
-def test_cheb_conv(gnn, be_unvalidated, k, weights):
-    be, rng = be_unvalidated, np.random.default_rng(0)
+def test_cheb_conv(gnn, be, k, weights):
+    be, rng = be, np.random.default_rng(0)
     g, s, t, A = setup(gnn, rng, be.dev, weights=weights, bidirected=True)       # symmetric, as scaled_laplacian assumes
     n, Din, Dout = g.num_nodes, 4, 3
     layer = gnn.ChebConv(Din, Dout, k, device=be.dev)
@@ -106,8 +105,8 @@ def test_cheb_conv(gnn, be_unvalidated, k, weights):
 
 
 @pytest.mark.parametrize("aggr", ["max", "+"])
-def test_edge_conv(gnn, be_unvalidated, aggr):
-    be, rng = be_unvalidated, np.random.default_rng(1)
+def test_edge_conv(gnn, be, aggr):
+    be, rng = be, np.random.default_rng(1)
     g, s, t, A = setup(gnn, rng, be.dev, simple=True)     # with repeated edges NNlib's max pullback feeds every tied
     n, Din, Dout = g.num_nodes, 4, 5                      # message, torch's amax splits the gradient: not comparable
     nn = gnn.layers._DenseAct(2 * Din, Dout, torch.tanh, device=be.dev)
@@ -125,8 +124,8 @@ def test_edge_conv(gnn, be_unvalidated, aggr):
     grads_match(gnn, out, xt, ref, xr, 3e-5 * be.tol)
 
 
-def test_nn_conv(gnn, be_unvalidated):
-    be, rng = be_unvalidated, np.random.default_rng(2)
+def test_nn_conv(gnn, be):
+    be, rng = be, np.random.default_rng(2)
     g, s, t, A = setup(gnn, rng, be.dev)
     n, E, Din, Dout, De = g.num_nodes, g.num_edges, 3, 4, 2
     nn = gnn.layers._Dense(De, Dout * Din, device=be.dev)
@@ -144,8 +143,8 @@ def test_nn_conv(gnn, be_unvalidated):
     grads_match(gnn, out, xt, ref, xr, 3e-5 * be.tol)
 
 
-def test_res_gated_and_cg_conv(gnn, be_unvalidated):
-    be, rng = be_unvalidated, np.random.default_rng(3)
+def test_res_gated_and_cg_conv(gnn, be):
+    be, rng = be, np.random.default_rng(3)
     g, s, t, A = setup(gnn, rng, be.dev)
     n, E, Din, Dout, De = g.num_nodes, g.num_edges, 4, 4, 3
     x, e = rng.standard_normal((n, Din)), rng.standard_normal((E, De))
@@ -171,8 +170,8 @@ def test_res_gated_and_cg_conv(gnn, be_unvalidated):
         layer(g, xt, jl(gnn, e[:-1], be.dev))
 
 
-def test_megnet_conv(gnn, be_unvalidated):
-    be, rng = be_unvalidated, np.random.default_rng(4)
+def test_megnet_conv(gnn, be):
+    be, rng = be, np.random.default_rng(4)
     g, s, t, A = setup(gnn, rng, be.dev)
     n, E, Din, Dout = g.num_nodes, g.num_edges, 3, 5
     layer = gnn.MEGNetConv(Din, Dout, device=be.dev)
@@ -189,8 +188,8 @@ def test_megnet_conv(gnn, be_unvalidated):
 
 
 @pytest.mark.parametrize("K,residual", [(1, False), (3, True)])
-def test_gmm_conv(gnn, be_unvalidated, K, residual):
-    be, rng = be_unvalidated, np.random.default_rng(5)
+def test_gmm_conv(gnn, be, K, residual):
+    be, rng = be, np.random.default_rng(5)
     g, s, t, A = setup(gnn, rng, be.dev)
     n, E, Din, ein = g.num_nodes, g.num_edges, 4, 2
     Dout = Din if residual else 3
@@ -213,8 +212,8 @@ def test_gmm_conv(gnn, be_unvalidated, K, residual):
 
 
 @pytest.mark.parametrize("ein,residual", [(0, False), (2, True)])
-def test_egnn_conv(gnn, be_unvalidated, ein, residual):
-    be, rng = be_unvalidated, np.random.default_rng(6)
+def test_egnn_conv(gnn, be, ein, residual):
+    be, rng = be, np.random.default_rng(6)
     g, s, t, A = setup(gnn, rng, be.dev, loops=False)
     n, E, hin, Dx = g.num_nodes, g.num_edges, 5, 3
     layer = gnn.EGNNConv((hin, ein), hin, hidden_size=6, residual=residual, device=be.dev)
@@ -244,8 +243,8 @@ def test_egnn_conv(gnn, be_unvalidated, ein, residual):
 
 
 @pytest.mark.parametrize("k,weights", [(1, False), (2, True), (3, False)])
-def test_d_conv(gnn, be_unvalidated, k, weights):
-    be, rng = be_unvalidated, np.random.default_rng(7)
+def test_d_conv(gnn, be, k, weights):
+    be, rng = be, np.random.default_rng(7)
     g, s, t, A = setup(gnn, rng, be.dev, weights=weights)
     n, Din, Dout = g.num_nodes, 3, 4
     layer = gnn.DConv(Din, Dout, k, device=be.dev)

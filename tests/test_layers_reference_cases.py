@@ -2,8 +2,7 @@
 repo: constructor fields and trainable-parameter counts, output sizes on TEST_GRAPHS (test_module.jl:159-180: the
 4-cycle and the graph with an isolated vertex; COO only — dense / sparse adjacency graphs are outside the path), and
 gradients that exist and are finite (the exact gradient values are checked in tests/test_layers.py).
-Both back ends of the `be` fixture; the cuda variants are new and stay skipped until they have run once
-(GNNB_RUN_UNVALIDATED=1)."""
+Both back ends of the `be` fixture."""
 import operator
 
 import pytest
@@ -38,8 +37,8 @@ def check(gnn, layer, g, *inputs, size):
         assert p.grad is None or torch.isfinite(p.grad).all()
 
 
-def test_gcnconv(gnn, be_unvalidated):                                              # conv.jl:7-66
-    dev = be_unvalidated.dev
+def test_gcnconv(gnn, be):                                              # conv.jl:7-66
+    dev = be.dev
     for g in ref_graphs(gnn, dev):
         for kw in (dict(), dict(sigma=torch.tanh, bias=False), dict(sigma=torch.tanh, add_self_loops=False)):
             if kw.get("add_self_loops") is False and g.num_edges == 4:
@@ -67,8 +66,8 @@ def test_gcnconv(gnn, be_unvalidated):                                          
     assert ww.grad.shape == (6,) and ww.grad.dtype == torch.float32
 
 
-def test_graphconv_sage_gin(gnn, be_unvalidated):                                   # conv.jl:122-141, 277-288, 327-337
-    dev = be_unvalidated.dev
+def test_graphconv_sage_gin(gnn, be):                                   # conv.jl:122-141, 277-288, 327-337
+    dev = be.dev
     assert ntrainable(gnn.GraphConv(2, 3)) == 3 and ntrainable(gnn.GraphConv(2, 3, bias=False)) == 2
     assert gnn.SAGEConv(D_IN, D_OUT).aggr is gnn.mean
     for g in ref_graphs(gnn, dev):
@@ -83,8 +82,8 @@ def test_graphconv_sage_gin(gnn, be_unvalidated):                               
 
 
 @pytest.mark.parametrize("cls", ["GATConv", "GATv2Conv"])
-def test_attention_layers(gnn, be_unvalidated, cls):                                # conv.jl:154-180, 194-220
-    dev = be_unvalidated.dev
+def test_attention_layers(gnn, be, cls):                                # conv.jl:154-180, 194-220
+    dev = be.dev
     L = getattr(gnn, cls)
     for heads in (1, 2):
         for concat in (True, False):
@@ -103,16 +102,16 @@ def test_attention_layers(gnn, be_unvalidated, cls):                            
         assert ntrainable(gnn.GATConv(2, 3)) == 3 and ntrainable(gnn.GATConv(2, 3, bias=False)) == 2
 
 
-def test_gated_graph_conv(gnn, be_unvalidated):                                     # conv.jl:234-245
-    dev = be_unvalidated.dev
+def test_gated_graph_conv(gnn, be):                                     # conv.jl:234-245
+    dev = be.dev
     l = gnn.GatedGraphConv(D_OUT, 3, aggr=gnn.mean, device=dev)
     assert tuple(l.weight.shape) == (D_OUT, D_OUT, 3)
     for g in ref_graphs(gnn, dev):
         check(gnn, l, g, g.x, size=(D_OUT, 4))
 
 
-def test_agnnconv(gnn, be_unvalidated):                                             # conv.jl:398-415
-    dev = be_unvalidated.dev
+def test_agnnconv(gnn, be):                                             # conv.jl:398-415
+    dev = be.dev
     l = gnn.AGNNConv(trainable=False, add_self_loops=False)
     assert l.beta.tolist() == [1.0] and l.add_self_loops is False and l.trainable is False and ntrainable(l) == 0
     l = gnn.AGNNConv(init_beta=2.0, device=dev)
@@ -122,16 +121,16 @@ def test_agnnconv(gnn, be_unvalidated):                                         
 
 
 @pytest.mark.parametrize("cls", ["SGConv", "TAGConv"])
-def test_sg_tag_conv(gnn, be_unvalidated, cls):                                     # conv.jl:485-530
-    dev = be_unvalidated.dev
+def test_sg_tag_conv(gnn, be, cls):                                     # conv.jl:485-530
+    dev = be.dev
     for k in (1, 2, 3):
         l = getattr(gnn, cls)(D_IN, D_OUT, k, add_self_loops=True, device=dev)
         for g in ref_graphs(gnn, dev):
             check(gnn, l, g, g.x, size=(D_OUT, 4))
 
 
-def test_transformer_conv(gnn, be_unvalidated):                                     # conv.jl:561-591
-    dev = be_unvalidated.dev
+def test_transformer_conv(gnn, be):                                     # conv.jl:561-591
+    dev = be.dev
     ein, heads = 2, 3
     l = gnn.TransformerConv(D_IN * heads, D_IN, heads=heads, add_self_loops=True, root_weight=False, ff_channels=10,
                             skip_connection=True, batch_norm=False, device=dev)         # Kool et al., 2019

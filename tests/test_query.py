@@ -8,8 +8,8 @@ def T(a, dev):
     return torch.tensor(a).to(dev)
 
 
-def test_symmetric_graph(gnn, be_unvalidated):                          # gnngraph.jl:42-83
-    dev = be_unvalidated.dev
+def test_symmetric_graph(gnn, be):                          # gnngraph.jl:42-83
+    dev = be.dev
     s, t = [1, 1, 2, 2, 3, 3, 4, 4], [2, 4, 1, 3, 2, 4, 1, 3]
     adj = [[0, 1, 0, 1], [1, 0, 1, 0], [0, 1, 0, 1], [1, 0, 1, 0]]
     g = gnn.GNNGraph(T(s, dev), T(t, dev))
@@ -29,8 +29,8 @@ def test_symmetric_graph(gnn, be_unvalidated):                          # gnngra
     assert a.tolist() == s and b.tolist() == t
 
 
-def test_asymmetric_graph(gnn, be_unvalidated):                         # gnngraph.jl:128-168
-    dev = be_unvalidated.dev
+def test_asymmetric_graph(gnn, be):                         # gnngraph.jl:128-168
+    dev = be.dev
     s, t = [1, 2, 3, 4], [2, 3, 4, 1]
     g = gnn.GNNGraph(T(s, dev), T(t, dev))
     assert g.num_edges == 4 and g.num_nodes == 4
@@ -44,8 +44,8 @@ def test_asymmetric_graph(gnn, be_unvalidated):                         # gnngra
     assert not gnn.is_bidirected(g)
 
 
-def test_adjacency_list_with_eid_and_flags(gnn, be_unvalidated):        # query.jl:176-198, 553-579
-    dev = be_unvalidated.dev
+def test_adjacency_list_with_eid_and_flags(gnn, be):        # query.jl:176-198, 553-579
+    dev = be.dev
     s, t = [3, 1, 3, 2, 2, 3], [1, 2, 1, 2, 3, 4]                       # a repeated edge (3 -> 1) and a self loop (2 -> 2)
     w = torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0, 6.0]).to(dev)
     g = gnn.GNNGraph(T(s, dev), T(t, dev), w)

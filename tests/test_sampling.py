@@ -4,8 +4,7 @@ The reference draws from Julia's RNG, so these are the size-independent properti
 and GNNGraphs/test/sampling.jl (every sampled edge is an in/out-edge of its node, counts = min(K, deg) or K, no
 repeats without replacement, EID / NID bookkeeping, induced subgraphs), plus a uniformity check of the subset sampler.
 
-Back ends: the CPU test double always; the CUDA kernels of csrc/sample.cu were written after the round's GPU budget
-was spent, so their variant is skipped unless GNNB_RUN_UNVALIDATED=1 (first thing to run in the next round).
+Back ends: the CPU test double and (under -m gpu) the CUDA kernels of csrc/sample.cu.
 """
 import numpy as np
 import pytest
@@ -13,8 +12,8 @@ import torch
 
 
 @pytest.fixture
-def bs(be_unvalidated):
-    return be_unvalidated
+def bs(be):
+    return be
 
 
 def idx(a, dev):
