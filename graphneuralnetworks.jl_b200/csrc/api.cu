@@ -94,7 +94,7 @@ int gnnb_device_count(void) {
 }
 int64_t gnnb_launch_count(void) { return g_launches.load(); }
 int gnnb_set_kernel_variant(int v) {
-    if (v < 0 || v > 9) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be in [0,9]");
+    if (v != 0 && v != 1 && v != 5 && v != 10 && v != 12) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be one of 0, 1, 5, 10, 12");
     gnnb::g_variant = v;
     return GNNB_OK;
 }
@@ -165,7 +165,20 @@ int gnnb_gcn_propagate(gnnb_graph_t g, int transposed, const float* x, const flo
                        int64_t D, float* out, void* stream) {
     if (!g) GNNB_FAIL(GNNB_EINVAL, "graph handle is NULL");
     if (g->n_src != g->n_dst) GNNB_FAIL(GNNB_ESIZE, "gcn_propagate needs num_src == num_dst");
-    if (!c) GNNB_FAIL(GNNB_EINVAL, "c (from gnnb_gcn_norm) is NULL");
+    if (!c) {
+        // the plan's own default normalisation c = 1/sqrt(in-degree) (unweighted): plan-owned, immutable, and with it the
+        // per-edge stream es[e] = c[col[e]] that spares the kernel a dependent 4 B gather per edge
+        if (w) GNNB_FAIL(GNNB_EINVAL, "c is NULL: the plan-owned normalisation exists for unweighted graphs only");
+        if (!x || !out) GNNB_FAIL(GNNB_EINVAL, "x/out is NULL");
+        if (D <= 0) GNNB_FAIL(GNNB_ESIZE, "feature dimension must be positive (got %lld)", (long long)D);
+        cudaStream_t st = (cudaStream_t)stream;
+        GNNB_TRY(ensure_csr(g, transposed != 0, st));
+        GNNB_TRY(ensure_gcn_scale(g, transposed != 0, st));
+        const Csr& cc = transposed ? g->by_src : g->by_dst;
+        SegArgs a;
+        a.x = x; a.cs = g->gcn_c; a.es = cc.es; a.ct = g->gcn_c; a.out = out; a.D = D; a.aggr = GNNB_SUM;
+        return seg_reduce(g, cc, a, st);
+    }
     return gnnb_propagate(g, transposed, w ? GNNB_W_MUL_XJ : GNNB_COPY_XJ, GNNB_SUM, x, w, c, c, D, out, stream);
 }
 

@@ -56,7 +56,12 @@ struct Csr {
     int32_t nrows = 0;  // reduction rows (targets; sources when transposed)
     int32_t ncols = 0;  // gathered nodes
     float* invdeg = nullptr;  // lazily: 1/max(deg,1) per row (for MEAN)
-    int32_t* chunk_info = nullptr;  // lazily (kernel variants 8, 9): 4 ints per chunk = chunk_bounds() precomputed
+    // lazily (seglean.cu): the chunk decomposition as a compact list of work items {e_begin, e_end, slot, 0}: slot < 0 = whole
+    // rows (stored at every row end), slot >= 0 = one piece of a long row (raw partial into workspace slot `slot`)
+    int32_t* items = nullptr;
+    int32_t n_items = 0;
+    int32_t n_empty = -1;     // rows without edges (-1 = not counted yet)
+    float* es = nullptr;      // lazily: es[e] = node_scale[col[e]] in plan order (the plan-owned GCN normalisation)
     bool built = false;
 };
 
@@ -76,6 +81,7 @@ struct gnnb_graph {
     size_t ws_bytes = 0;
     float* ws2 = nullptr;
     size_t ws2_bytes = 0;
+    float* gcn_c = nullptr;      // lazily: 1/sqrt(in-degree), the default symmetric normalisation (unweighted), plan-owned
     std::mutex mu;
 };
 
@@ -84,6 +90,8 @@ int ensure_ws(gnnb_graph* g, size_t bytes);
 int ensure_ws2(gnnb_graph* g, size_t bytes);
 int ensure_csr(gnnb_graph* g, bool transposed, cudaStream_t st);
 int ensure_invdeg(gnnb_graph* g, Csr& c, cudaStream_t st);
+int ensure_items(gnnb_graph* g, const Csr& c, cudaStream_t st);            // seglean.cu
+int ensure_gcn_scale(gnnb_graph* g, bool transposed, cudaStream_t st);     // seglean.cu: g->gcn_c and the Csr's es stream
 
 // segreduce.cu
 struct SegArgs {
@@ -92,6 +100,7 @@ struct SegArgs {
     int32_t split = 0;
     const float* w = nullptr;   // per-edge weight in PLAN order or nullptr
     const float* cs = nullptr;  // per gathered-node scale or nullptr
+    const float* es = nullptr;  // the same scale already gathered per edge (plan order): es[e] == cs[col[e]]; needs cs too
     const float* ct = nullptr;  // per output-row scale or nullptr
     float* out = nullptr;       // [nrows][D]
     int64_t D = 0;

@@ -92,7 +92,7 @@ __global__ void selfloop_rows_kernel(const int32_t* __restrict__ rowptr, int32_t
 // ---- helpers ------------------------------------------------------------------------------------
 static void free_csr(Csr& c) {
     cudaFree(c.rowptr); cudaFree(c.col); cudaFree(c.row); cudaFree(c.eid);
-    cudaFree(c.long_rows); cudaFree(c.invdeg); cudaFree(c.chunk_info);
+    cudaFree(c.long_rows); cudaFree(c.invdeg); cudaFree(c.items); cudaFree(c.es);
     c = Csr();
 }
 
@@ -284,6 +284,7 @@ int gnnb_graph_destroy(gnnb_graph_t g) {
     free_csr(g->by_src);
     cudaFree(g->ws);
     cudaFree(g->ws2);
+    cudaFree(g->gcn_c);
     delete g;
     return GNNB_OK;
 }

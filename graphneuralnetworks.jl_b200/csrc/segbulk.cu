@@ -232,167 +232,8 @@ static int launch_bulk(const BulkParams& p, cudaStream_t st) {
     return GNNB_OK;
 }
 
-// ======================================================================================================
-// cp.async (LDGSTS) staged variant.  Measured on B200 (gpurun_out/sweep1.log, profiles/r1_seg_variants.md): the
-// UBLKCP path above is TMA-unit bound at roughly one 512 B row per 56-100 cycles per SM (22-41 ms vs 10 ms for the
-// register-staged kernel) — small bulk copies are the wrong tool.  LDGSTS keeps the idea (rows land in shared
-// memory, not in registers; depth bounded by smem) with one warp-wide 16 B-per-lane copy per row: every lane copies
-// and later reads back only ITS OWN 16 bytes of each row, so the ring is a per-lane FIFO that needs no barrier at
-// all — `cp.async.wait_group` is the only synchronisation.  Indices/scales of a 128-edge window live in shared
-// memory and are read by broadcast LDS instead of shuffles.
-// ======================================================================================================
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// K float4 slices per lane (D = 128 K); RING rows per warp; G rows per commit group; L groups of lookahead
-template <int K, int RING, int L, int WARPS, bool ISMAX>
-__global__ void __launch_bounds__(32 * WARPS) seg_reduce_async_kernel(const BulkParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int G = 8;
-    constexpr int IW = 128;                            // index window (edges)
-    constexpr int RB = K * 512;
-    constexpr int WARP_BYTES = RING * RB + IW * 12;
-    static_assert(RING >= (L + 1) * G, "ring too small for the lookahead");
-    static_assert(IW >= L * G + 64, "index window too small");
-    const int lane = threadIdx.x & 31;
-    const int wid = threadIdx.x >> 5;
-    const int64_t k = (int64_t)blockIdx.x * WARPS + wid;
-    unsigned char* wbase = smem_raw + (size_t)wid * WARP_BYTES;
-    const float* ring = reinterpret_cast<const float*>(wbase);
-    int32_t* sm_c = reinterpret_cast<int32_t*>(wbase + RING * RB);
-    int32_t* sm_d = sm_c + IW;
-    float* sm_s = reinterpret_cast<float*>(sm_d + IW);
-    const uint32_t ring0 = smem_u32(wbase) + lane * 16;
-    const float neutral = ISMAX ? -CUDART_INF_F : 0.f;
-    const float fillv = ISMAX ? (p.sign < 0.f ? CUDART_INF_F : -CUDART_INF_F) : 0.f;
-
-    const ChunkBounds cb = chunk_bounds(p.rowptr, p.row, k, p.chunk, p.E, p.nchunks);
-    const int e_begin = cb.e_begin, e_end = cb.e_end;
-    const int nE = e_end - e_begin;
-    if (nE <= 0) return;
-    const int nbatch = (nE + 31) >> 5;
-    const int ngroups = (nE + G - 1) / G;
-
-    float4 acc[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) acc[i] = make_float4(neutral, neutral, neutral, neutral);
-    int r = -1;
-    bool first_flush = true;
-    auto flush = [&](int rr, bool last) {
-        float* base;
-        bool raw;
-        if (first_flush && cb.head_partial) { base = p.ws + (size_t)(2 * k + 0) * p.D; raw = true; }
-        else if (last && cb.tail_partial) { base = p.ws + (size_t)(2 * k + 1) * p.D; raw = true; }
-        else { base = p.out + (size_t)rr * p.D; raw = false; }
-        first_flush = false;
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const float4 v = raw ? acc[i] : bfinish(acc[i], p, rr);
-            *reinterpret_cast<float4*>(base + i * 128 + lane * 4) = v;
-        }
-    };
-    auto fill_gap = [&](int lo, int hi) {
-        if (!p.fill) return;
-        for (int q = lo + 1; q < hi; ++q)
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-                *reinterpret_cast<float4*>(p.out + (size_t)q * p.D + i * 128 + lane * 4) =
-                    make_float4(fillv, fillv, fillv, fillv);
-    };
-
-    // index batches: loaded into registers one batch ahead, published to the shared window when needed
-    int n_c = 0, n_d = -1;
-    float n_s = 1.f;
-    auto load_idx = [&](int b) {
-        const int my_e = e_begin + b * 32 + lane;
-        n_c = 0; n_d = -1; n_s = 1.f;
-        if (b < nbatch && my_e < e_end) {
-            n_c = __ldg(p.col + my_e);
-            n_d = __ldg(p.row + my_e);
-            if (p.cs) n_s = __ldg(p.cs + n_c);
-            if (p.w) n_s = __fmul_rn(n_s, __ldg(p.w + my_e));
-            if (p.sign < 0.f) n_s = -n_s;
-        }
-    };
-    int published = 0;                                  // batches whose indices are in the window
-    auto publish = [&]() {                              // registers (batch `published`) -> window; prefetch the next
-        const int slot = (published * 32 + lane) & (IW - 1);
-        sm_c[slot] = n_c; sm_d[slot] = n_d; sm_s[slot] = n_s;
-        ++published;
-        load_idx(published);
-        __syncwarp();
-    };
-    auto issue_group = [&](int gi) {                    // G row copies + one commit (an empty group still commits)
-        if (gi < ngroups) {
-            while (published * 32 < min(nE, (gi + 1) * G)) publish();
-#pragma unroll
-            for (int u = 0; u < G; ++u) {
-                const int q = gi * G + u;
-                if (q < nE) {
-                    const int cj = sm_c[q & (IW - 1)];
-                    const float* src = (p.x2 != nullptr && cj >= p.split) ? p.x2 + (size_t)(cj - p.split) * p.D
-                                                                          : p.x + (size_t)cj * p.D;
-                    const uint32_t dst = ring0 + (uint32_t)((q & (RING - 1)) * RB);
-#pragma unroll
-                    for (int i = 0; i < K; ++i) cp_async16(dst + i * 512, src + i * 128 + lane * 4);
-                }
-            }
-        }
-        cp_async_commit();
-    };
-
-    load_idx(0);
-#pragma unroll 1
-    for (int gi = 0; gi < L; ++gi) issue_group(gi);
-#pragma unroll 1
-    for (int gi = 0; gi < ngroups; ++gi) {
-        issue_group(gi + L);
-        cp_async_wait<L>();                             // group gi has landed (this lane's 16 B of each row)
-#pragma unroll
-        for (int u = 0; u < G; ++u) {
-            const int q = gi * G + u;
-            if (q < nE) {                               // warp-uniform
-                const int dj = sm_d[q & (IW - 1)];
-                if (dj != r) {
-                    if (r >= 0) { flush(r, false); fill_gap(r, dj); }
-                    else if (!cb.head_partial) fill_gap(cb.prev_row, dj);
-                    r = dj;
-#pragma unroll
-                    for (int i = 0; i < K; ++i) acc[i] = make_float4(neutral, neutral, neutral, neutral);
-                }
-                const float sj = sm_s[q & (IW - 1)];
-                const float* rowp = ring + (size_t)(q & (RING - 1)) * (RB / 4) + lane * 4;
-#pragma unroll
-                for (int i = 0; i < K; ++i) acc[i] = bcomb<ISMAX>(acc[i], *reinterpret_cast<const float4*>(rowp + i * 128), sj);
-            }
-        }
-    }
-    flush(r, true);
-    if (e_end == p.E) fill_gap(r, p.nrows);
-}
-
-template <int K, int RING, int L, int WARPS, bool ISMAX>
-static int launch_async(const BulkParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)WARPS * (RING * K * 512 + 128 * 12);
-    static bool configured = false;
-    if (!configured) {
-        GNNB_CUDA(cudaFuncSetAttribute(seg_reduce_async_kernel<K, RING, L, WARPS, ISMAX>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const unsigned grid = (unsigned)ceil_div(p.nchunks, WARPS);
-    seg_reduce_async_kernel<K, RING, L, WARPS, ISMAX><<<grid, 32 * WARPS, smem, st>>>(p);
-    GNNB_LAUNCHED();
-    return GNNB_OK;
-}
-
 // returns GNNB_EUNSUPPORTED (without setting the error text) when the shape is not covered.
-// cfg: 0 = UBLKCP ring (2 stages x 3 warps); 1..3 = LDGSTS ring (RING rows, L groups of 8 ahead, warps per CTA)
+// (the cp.async / LDGSTS ring variants measured in round 1 — 1.5-4x slower, profiles/r1_seg_variants.md — are gone)
 int seg_reduce_bulk(const Csr& c, const SegArgs& a, int64_t E, int chunk, float* ws, int fill, int cfg,
                     cudaStream_t st) {
     if (a.D % 128 != 0 || a.D > 512 || a.D == 384) return GNNB_EUNSUPPORTED;
@@ -405,27 +246,11 @@ int seg_reduce_bulk(const Csr& c, const SegArgs& a, int64_t E, int chunk, float*
     const int K = (int)(a.D / 128);
 #define BULK_CASE(KK, SS, WW) \
     return ismax ? launch_bulk<KK, SS, WW, true>(p, st) : launch_bulk<KK, SS, WW, false>(p, st);
-#define ASYNC_CASE(KK, RR, LL, WW) \
-    return ismax ? launch_async<KK, RR, LL, WW, true>(p, st) : launch_async<KK, RR, LL, WW, false>(p, st);
-    if (cfg == 0) {
-        if (K == 1) { BULK_CASE(1, 2, 3) }
-        if (K == 2) { BULK_CASE(2, 3, 1) }
-        BULK_CASE(4, 2, 1)
-    }
-    if (K == 1) {
-        if (cfg == 1) { ASYNC_CASE(1, 64, 6, 3) }      // 32 KB ring/warp, 48 rows ahead, 6 warps/SM
-        if (cfg == 2) { ASYNC_CASE(1, 32, 3, 4) }      // 16 KB ring/warp, 24 rows ahead, 12 warps/SM
-        ASYNC_CASE(1, 16, 1, 8)                        // 8 KB ring/warp, 8 rows ahead, 24 warps/SM
-    }
-    if (K == 2) {
-        if (cfg == 1) { ASYNC_CASE(2, 32, 3, 3) }
-        if (cfg == 2) { ASYNC_CASE(2, 16, 1, 4) }
-        ASYNC_CASE(2, 16, 1, 6)
-    }
-    if (cfg == 1) { ASYNC_CASE(4, 16, 1, 3) }
-    ASYNC_CASE(4, 16, 1, 2)
+    (void)cfg;
+    if (K == 1) { BULK_CASE(1, 2, 3) }
+    if (K == 2) { BULK_CASE(2, 3, 1) }
+    BULK_CASE(4, 2, 1)
 #undef BULK_CASE
-#undef ASYNC_CASE
 }
 
 }  // namespace gnnb

@@ -30,8 +30,12 @@ namespace gnnb {
 
 // SegParams: segparams.cuh
 
-// kernel variant: 0 = register-staged kernel (default); 1 = UBLKCP ring, 2..4 = LDGSTS rings (segbulk.cu);
-// 5 = register-staged kernel without the 64-register cap; 6, 7 = index-prefetch kernel (segprefetch.cu); 8, 9 = the same reading chunk bounds precomputed in the plan
+// kernel variant (gnnb_set_kernel_variant, A/B runs): 0 = default: the lean work-item kernel (seglean.cu) for rows of
+// 128 / 256 / 512 floats, taking the per-edge scale stream when the caller has one, and seg_reduce_kernel below for every
+// other shape; 10 = the lean kernel gathering cs[col] itself; 12 = seg_reduce_kernel everywhere (the round-1 default);
+// 5 = the same without the 64-register cap; 1 = shared-memory ring filled by cp.async.bulk (segbulk.cu).
+// Round 1's LDGSTS rings (2..4) and round 2's index-prefetch variants (6..9) were measured slower and removed
+// (profiles/r1_seg_variants.md, profiles/r2_seg_lean.md).
 int g_variant = 0;
 
 template <int VEC> struct VecT;
@@ -240,12 +244,6 @@ __global__ void fill_empty_rows_kernel(const int32_t* __restrict__ rowptr, float
     if (rowptr[r] == rowptr[r + 1]) out[i] = v;
 }
 
-// segprefetch.cu (A/B variants 6..9); the chunk table travels beside SegParams so that the struct — and with it the
-// code of every measured kernel — stays exactly as it was
-int launch_seg_prefetch(const SegParams& p, const int32_t* chunk_info, bool ismax, int loads, dim3 grid, cudaStream_t st);
-int ensure_chunk_info(gnnb_graph* g, const Csr& c, const int32_t** out, cudaStream_t st);
-static thread_local const int32_t* g_chunk_info = nullptr;   // set by seg_reduce() for the launch that follows
-
 template <int VEC, int TPR, int K, bool ISMAX>
 static int launch_seg(const SegParams& p, cudaStream_t st) {
     const int gpb = 256 / TPR;  // groups per block
@@ -253,8 +251,6 @@ static int launch_seg(const SegParams& p, cudaStream_t st) {
     // One warp per 512 B row (D = 128 fp32): throughput follows the number of resident warps, not the loads per warp
     // (profiles/r1_seg_variants.md): cap the kernel at 64 registers => 4 CTAs x 8 warps per SM.  Variant 5 keeps the
     // uncapped build (77 registers, 24 warps) for A/B runs.
-    if (VEC == 4 && TPR == 32 && K == 1 && g_variant >= 6 && g_variant <= 9)
-        return launch_seg_prefetch(p, g_chunk_info, ISMAX, (g_variant & 1) ? 6 : 8, grid, st);
     if (VEC == 4 && TPR == 32 && K == 1 && g_variant != 5) {
         seg_reduce_kernel<4, 32, 1, ISMAX, 8, 4><<<grid, 256, 0, st>>>(p);
         GNNB_LAUNCHED();
@@ -283,6 +279,7 @@ static int pow2ceil(int64_t v) {
 }
 
 int seg_reduce_bulk(const Csr& c, const SegArgs& a, int64_t E, int chunk, float* ws, int fill, int cfg, cudaStream_t st);
+int seg_reduce_lean(gnnb_graph* g, const Csr& c, const SegArgs& a, float* ws, bool use_es, cudaStream_t st);   // seglean.cu
 
 int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
     if (a.D <= 0) GNNB_FAIL(GNNB_ESIZE, "feature dimension must be positive (got %lld)", (long long)a.D);
@@ -303,31 +300,35 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
     p.mean = (a.aggr == GNNB_MEAN);
     p.sign = (a.aggr == GNNB_MIN) ? -1.f : 1.f;
     p.fill = 1;
-    if ((int64_t)c.nrows > 4 * g->E) {
+    p.ws = nullptr;
+    if (c.n_long > 0) {
+        GNNB_TRY(ensure_ws(g, (size_t)2 * p.nchunks * a.D * sizeof(float)));
+        p.ws = g->ws;
+    }
+    // the lean work-item kernel (seglean.cu) for rows of 128 / 256 / 512 floats
+    int lean_rc = GNNB_EUNSUPPORTED;
+    if (g_variant == 0 || g_variant == 10) {
+        lean_rc = seg_reduce_lean(g, c, a, p.ws, g_variant == 0, st);
+        if (lean_rc != GNNB_OK && lean_rc != GNNB_EUNSUPPORTED) return lean_rc;
+    }
+    if (lean_rc != GNNB_OK && (int64_t)c.nrows > 4 * g->E) {
         p.fill = 0;
         float v = a.aggr == GNNB_MAX ? -HUGE_VALF : (a.aggr == GNNB_MIN ? HUGE_VALF : 0.f);
         int64_t n = (int64_t)c.nrows * a.D;
         fill_empty_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(c.rowptr, a.out, c.nrows, a.D, v);
         GNNB_LAUNCHED();
     }
-    g_chunk_info = nullptr;
-    if (g_variant == 8 || g_variant == 9) GNNB_TRY(ensure_chunk_info(g, c, &g_chunk_info, st));   // segprefetch.cu
-    p.ws = nullptr;
-    if (c.n_long > 0) {
-        GNNB_TRY(ensure_ws(g, (size_t)2 * p.nchunks * a.D * sizeof(float)));
-        p.ws = g->ws;
-    }
     const bool vec4 = (a.D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.x2) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     int tpr, k;
     int bulk_rc = GNNB_EUNSUPPORTED;
-    if (vec4 && g_variant >= 1 && g_variant <= 4) {
-        bulk_rc = seg_reduce_bulk(c, a, g->E, g->chunk, p.ws, p.fill, g_variant - 1, st);
+    if (lean_rc != GNNB_OK && vec4 && g_variant == 1) {
+        bulk_rc = seg_reduce_bulk(c, a, g->E, g->chunk, p.ws, p.fill, 0, st);
         if (bulk_rc != GNNB_OK && bulk_rc != GNNB_EUNSUPPORTED) return bulk_rc;
     }
-    if (bulk_rc == GNNB_OK) {
-        // done by a shared-memory-staged kernel (segbulk.cu)
+    if (lean_rc == GNNB_OK || bulk_rc == GNNB_OK) {
+        // done by the lean kernel (seglean.cu) or a shared-memory-staged kernel (segbulk.cu)
     } else if (vec4) {
         int64_t nv = a.D / 4;
         tpr = (int)(nv >= 32 ? 32 : pow2ceil(nv));

@@ -170,7 +170,7 @@ def gcn_conv(l, g: GNNGraph, x: torch.Tensor, edge_weight: Optional[torch.Tensor
     use_w = bool(getattr(l, "use_edge_weight", False)) and g.w is not None
     if edge_weight is None and not use_w and norm_fn is None:
         plan = g.plan()
-        out = unrows(_GCNPropagateFn.apply(_f32(rows(xj), plan.device), plan, _gcn_c(g)))
+        out = unrows(_GCNPropagateFn.apply(_f32(rows(xj), plan.device), plan, None))   # c: the plan's own
     else:
         nf = norm_fn or default_norm_fn
         if edge_weight is not None:

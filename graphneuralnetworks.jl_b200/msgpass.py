@@ -191,15 +191,16 @@ class _PropagateFn(torch.autograd.Function):
 
 
 class _GCNPropagateFn(torch.autograd.Function):
-    """c .* propagate(copy_xj, g, +, xj = x .* c') with c = 1/sqrt(in-degree): gnnb_gcn_propagate (both ways)."""
+    """c .* propagate(copy_xj, g, +, xj = x .* c') with c = 1/sqrt(in-degree): gnnb_gcn_propagate (both ways).
+    c = None: the plan's own normalisation (the library keeps c and its per-edge stream with the plan)."""
 
     @staticmethod
     def forward(ctx, x_rows, plan, c):
         D = x_rows[0].numel() if x_rows.shape[0] else 1
         out = torch.empty_like(x_rows)
         with torch.cuda.device(plan.device):
-            _lib.check(lib.gnnb_gcn_propagate(plan.h, 0, x_rows.data_ptr(), None, c.data_ptr(), D, out.data_ptr(),
-                                              _stream(plan.device)))
+            _lib.check(lib.gnnb_gcn_propagate(plan.h, 0, x_rows.data_ptr(), None, None if c is None else c.data_ptr(), D,
+                                              out.data_ptr(), _stream(plan.device)))
         ctx.plan, ctx.D, ctx.c = plan, D, c
         return out
 
@@ -208,8 +209,9 @@ class _GCNPropagateFn(torch.autograd.Function):
         dout = dout.contiguous()
         dx = torch.empty_like(dout)
         with torch.cuda.device(ctx.plan.device):
-            _lib.check(lib.gnnb_gcn_propagate(ctx.plan.h, 1, dout.data_ptr(), None, ctx.c.data_ptr(), ctx.D,
-                                              dx.data_ptr(), _stream(ctx.plan.device)))
+            _lib.check(lib.gnnb_gcn_propagate(ctx.plan.h, 1, dout.data_ptr(), None,
+                                              None if ctx.c is None else ctx.c.data_ptr(), ctx.D, dx.data_ptr(),
+                                              _stream(ctx.plan.device)))
         return dx, None, None
 
 

@@ -161,7 +161,9 @@ int gnnb_softmax_edge_neighbors_bwd(gnnb_graph_t g, const float* alpha, const fl
  * `g` must already carry the self loops if the layer adds them (gnnb_graph_add_self_loops).
  * w NULL or E floats (COO order of g, loop weights included).  c_out (num_dst floats) receives c
  * (kept by the caller for the backward).  transposed=1 computes the pullback w.r.t. x given dout
- * and the forward's c:  dx = c .* (A^T-propagate(dout .* c)). */
+ * and the forward's c:  dx = c .* (A^T-propagate(dout .* c)).
+ * c == NULL (w must be NULL too): the plan's own c = 1 ./ sqrt.(in-degree), computed once and kept with the plan
+ * together with its per-edge stream c[s_k] in plan order, which spares the kernel one dependent gather per edge. */
 int gnnb_gcn_norm(gnnb_graph_t g, const float* w, float* c_out, void* stream);
 int gnnb_gcn_propagate(gnnb_graph_t g, int transposed, const float* x, const float* w,
                        const float* c, int64_t D, float* out, void* stream);

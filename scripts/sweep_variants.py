@@ -16,7 +16,7 @@ x = torch.randn(n, D, device=dev)
 out = torch.empty_like(x)
 res = []
 CHUNKS = [int(c) for c in os.environ.get('CHUNKS', '128').split(',')]
-VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '0,5,6,7,8,9').split(',')]
+VARIANTS = [int(v) for v in os.environ.get('VARIANTS', '12,10,0').split(',')]
 for chunk in CHUNKS:
     gnn._lib.check(lib.gnnb_set_chunk_edges(chunk))
     g = gnn.rmat_graph(n, E, 17, device=dev)
@@ -29,12 +29,12 @@ for chunk in CHUNKS:
         row = {"chunk": chunk, "variant": v}
         for tr in (0, 1):
             for _ in range(2):
-                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, c.data_ptr(), D, out.data_ptr(), None))
+                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, None if v == 0 else c.data_ptr(), D, out.data_ptr(), None))
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
             torch.cuda.synchronize()
             for a, b in evs:
                 a.record()
-                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, c.data_ptr(), D, out.data_ptr(), None))
+                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, None if v == 0 else c.data_ptr(), D, out.data_ptr(), None))
                 b.record()
             torch.cuda.synchronize()
             row["fwd_ms" if tr == 0 else "bwd_ms"] = sum(a.elapsed_time(b) for a, b in evs) / 5
@@ -42,7 +42,7 @@ for chunk in CHUNKS:
                 if ref is None:
                     ref = out.clone()
                 else:
-                    row["bit_identical_to_v0"] = bool(torch.equal(out, ref))
+                    row["bit_identical_to_first"] = bool(torch.equal(out, ref))
         print(json.dumps(row), flush=True)
         res.append(row)
     del g, g2, c

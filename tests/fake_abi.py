@@ -265,7 +265,14 @@ class FakeLib:
         self.calls.append("gnnb_gcn_propagate")
         p = self._p(h)
         n = p.nd
-        cv = _arr(c, (n,)).astype(np.float64)
+        if c is None:                                   # the plan-owned default normalisation (unweighted only)
+            assert w is None
+            d = np.zeros(n)
+            np.add.at(d, p.t, 1.0)
+            with np.errstate(divide="ignore"):
+                cv = 1.0 / np.sqrt(d)
+        else:
+            cv = _arr(c, (n,)).astype(np.float64)
         xv = _arr(x, (n, D)).astype(np.float64) * cv[:, None]
         src, dst = (p.s, p.t) if not transposed else (p.t, p.s)
         m = xv[src]

@@ -575,16 +575,16 @@ DEFAULT_VARIANT = 0
 @pytest.mark.parametrize("D", [128, 256, 512])
 @pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
 def test_tma_staged_variant_is_bit_identical(graph, oracle, gnn, variant, D, aggr):
-    """The cp.async.bulk/mbarrier kernel (segbulk.cu) against the register-staged one: same bits, every ring config."""
+    """The cp.async.bulk/mbarrier kernel (segbulk.cu, variant 1) against the register-staged one (12): same bits."""
     name, s, t, n, g = graph
     rng = np.random.default_rng(D)
     x = jl(rng.standard_normal((n, D)).astype(np.float32))
     w = torch.as_tensor(rng.random(len(s)).astype(np.float32) + 0.1).cuda()
-    variant(0)
+    variant(12)
     base = gnn.propagate(gnn.copy_xj, g, aggr, xj=x)
     base_w = gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w)
     assert rel(np_rows(base), oracle.propagate_unfused(aggr, s, t, n, np_rows(x).astype(np.float64))) < TOL
-    for v in (1, 2, 3, 4, 5):
+    for v in (1, 5, 0):
         variant(v)
         assert torch.equal(gnn.propagate(gnn.copy_xj, g, aggr, xj=x), base), f"variant {v}"
         assert torch.equal(gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w), base_w), f"variant {v} weighted"
@@ -604,7 +604,7 @@ def test_tma_staged_variant_large_chunks(gnn, oracle, variant):
             g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
             l = gnn.GCNConv(128, 128, device="cuda")
             outs = []
-            for v in (0, 1, 3, 5):
+            for v in (12, 1, 5, 0):
                 variant(v)
                 g2 = gnn.add_self_loops(g)
                 c = gnn.layers._gcn_c(g2)
@@ -621,6 +621,96 @@ def test_tma_staged_variant_large_chunks(gnn, oracle, variant):
         gnn._lib.lib.gnnb_set_chunk_edges(128)
 
 
+@pytest.mark.parametrize("D", [128, 256, 512])
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+def test_lean_kernel_is_bit_identical(graph, oracle, gnn, variant, D, aggr):
+    """The work-item kernel (seglean.cu, variants 0 / 10) against seg_reduce_kernel (variant 12): same bits for every message /
+    aggregation / scale combination, and both against the oracle."""
+    name, s, t, n, g = graph
+    lib = gnn._lib.lib
+    rng = np.random.default_rng(D + 1)
+    x = jl(rng.standard_normal((n, D)).astype(np.float32))
+    w = torch.as_tensor(rng.random(len(s)).astype(np.float32) + 0.1).cuda()
+    cs = torch.rand(n, device="cuda") + 0.5
+    ct = torch.rand(n, device="cuda") + 0.5
+    p = g.plan()
+    A = {"+": gnn._lib.SUM, "mean": gnn._lib.MEAN, "max": gnn._lib.MAX, "min": gnn._lib.MIN}[aggr]
+
+    def scaled(tr, wt):
+        out = torch.empty(n, D, device="cuda")
+        gnn._lib.check(lib.gnnb_propagate(p.h, tr, gnn._lib.W_MUL_XJ if wt is not None else gnn._lib.COPY_XJ, A,
+                                          gnn.rows(x).data_ptr(), None if wt is None else wt.data_ptr(), cs.data_ptr(),
+                                          ct.data_ptr(), D, out.data_ptr(), None))
+        return out
+
+    def run():
+        return [gnn.propagate(gnn.copy_xj, g, aggr, xj=x), gnn.propagate(gnn.e_mul_xj, g, aggr, xj=x, e=w),
+                scaled(0, None), scaled(1, None), scaled(0, w), scaled(1, w)]
+
+    variant(12)
+    base = run()
+    assert rel(np_rows(base[0]), oracle.propagate_unfused(aggr, s, t, n, np_rows(x).astype(np.float64))) < TOL
+    for v in (0, 10):
+        variant(v)
+        for i, (a, b) in enumerate(zip(run(), base)):
+            assert torch.equal(a, b), f"variant {v} case {i}"
+
+
+@pytest.mark.parametrize("D", [128, 256])
+def test_lean_kernel_gcn_plan_norm_and_chunks(gnn, oracle, variant, D):
+    """GCN core with the plan-owned normalisation (c = NULL: per-edge scale stream) on a graph with hubs (long rows, every
+    kind of work item), several chunk sizes: variants 0 / 10 == variant 12 bit for bit, forward and transposed."""
+    rng = np.random.default_rng(3)
+    n = 3000
+    s, t = make_graph(rng, n, 60000, hubs=2, hub_deg=5000)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    ref, _ = oracle.gcn_propagate(s2, t2, n, x.astype(np.float64))
+    lib = gnn._lib.lib
+    try:
+        for chunk in (32, 128, 1024):
+            gnn._lib.check(lib.gnnb_set_chunk_edges(chunk))
+            g2 = gnn.add_self_loops(gnn.GNNGraph(s, t, num_nodes=n).cuda())
+            c = gnn.layers._gcn_c(g2)
+            xr = torch.as_tensor(x).cuda()
+            outs = {}
+            for v, cp in ((12, c), (10, c), (0, c), (0, None), (12, None)):
+                variant(v)
+                for tr in (0, 1):
+                    out = torch.empty(n, D, device="cuda")
+                    gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, xr.data_ptr(), None,
+                                                          None if cp is None else cp.data_ptr(), D, out.data_ptr(), None))
+                    if tr == 0:
+                        assert rel(out.cpu().numpy(), ref) < TOL, (chunk, v)
+                    outs.setdefault(tr, []).append(out)
+            for tr in (0, 1):
+                assert all(torch.equal(outs[tr][0], o) for o in outs[tr][1:]), (chunk, tr)
+    finally:
+        lib.gnnb_set_chunk_edges(128)
+
+
+def test_lean_kernel_halo_bases(graph, gnn, variant):
+    """gnnb_propagate_halo through the lean kernel: two source bases, node scales gathered per edge"""
+    name, s, t, n, g = graph
+    lib = gnn._lib.lib
+    D = 128
+    rng = np.random.default_rng(9)
+    x = torch.as_tensor(rng.standard_normal((n, D)).astype(np.float32)).cuda()
+    n_local = n // 3
+    x_local, x_halo = x[:n_local].clone(), x[n_local:].clone()
+    cs = torch.rand(n, device="cuda") + 0.5
+    ct = torch.rand(n, device="cuda") + 0.5
+    p = g.plan()
+    outs = []
+    for v in (12, 0):
+        variant(v)
+        out = torch.empty_like(x)
+        gnn._lib.check(lib.gnnb_propagate_halo(p.h, gnn._lib.COPY_XJ, gnn._lib.SUM, x_local.data_ptr(), x_halo.data_ptr(),
+                                               n_local, None, cs.data_ptr(), ct.data_ptr(), D, out.data_ptr(), None))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("D", [5, 16, 128, 256])
 def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
     """gnnb_propagate_halo: sources < n_local read x_local, the rest x_halo (the [local | halo] space of a shard)."""
@@ -634,7 +724,7 @@ def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
     ct = torch.rand(n, device="cuda") + 0.5
     ref = torch.empty_like(x)
     p = g.plan()
-    for v in (0, 1, 5):
+    for v in (0, 1, 5, 12):
         variant(v)
         gnn._lib.check(lib.gnnb_propagate(p.h, 0, gnn._lib.COPY_XJ, gnn._lib.SUM, x.data_ptr(), None, cs.data_ptr(),
                                           ct.data_ptr(), D, ref.data_ptr(), None))
