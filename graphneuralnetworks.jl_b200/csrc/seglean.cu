@@ -25,7 +25,7 @@ namespace gnnb {
 
 struct LeanParams {
     const int4* __restrict__ items;
-    const int32_t* __restrict__ col;
+    const int32_t* __restrict__ col;     // gathered node of each edge ([x | x2] index space)
     const int32_t* __restrict__ row;
     const int32_t* __restrict__ rowptr;
     const float* __restrict__ es;   // SMODE 1: per-edge scale stream
@@ -144,9 +144,11 @@ __device__ __forceinline__ float4 lcomb(float4 a, float4 v, float s1, float s2, 
 }
 
 // KV float4 per lane: one warp covers a row of KV*128 floats.  SMODE 0: no gathered-node scale, 1: per-edge stream es,
-// 2: gather cs[col].  Everything that steers control flow is made warp-uniform through a vote (ballot / any), so that the
+// 2: gather cs[col].  HALO 0: one source base; 1: nodes >= split live in x2 (the halo rows of a shard).
+// (Staging the most gathered rows in a persisting-L2 window, with or without cache-streaming loads for the rest, was
+// measured 2-50 % slower: profiles/r2_seg_lean.md.)  Everything that steers control flow is made warp-uniform through a vote (ballot / any), so that the
 // compiler keeps the loop free of divergence handling; shuffles are never executed under a lane-dependent condition.
-template <int KV, int SMODE, bool HAS_W, bool HALO, int AGG>
+template <int KV, int SMODE, bool HAS_W, int HALO, int AGG>
 __global__ void __launch_bounds__(256, 4) seg_lean_kernel(const LeanParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int U = 8 / KV;                 // row loads a warp keeps in flight (4 KB)
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(256, 4) seg_lean_kernel(const LeanParams p) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int cj = __shfl_sync(FULL, c_l, j0 + u);
-                const float* xr = ((HALO && cj >= p.split) ? x2l : xl) + (int64_t)cj * STRIDE;
+                const bool second = HALO != 0 && cj >= p.split;
+                const float* xr = (second ? x2l : xl) + (int64_t)cj * STRIDE;
                 if ((vmask >> (j0 + u)) & 1u) {
 #pragma unroll
                     for (int i = 0; i < KV; ++i) v[u][i] = __ldg(reinterpret_cast<const float4*>(xr + i * 128));
@@ -231,8 +234,8 @@ __global__ void __launch_bounds__(256, 4) seg_lean_kernel(const LeanParams p) {
                     }
 #pragma unroll
                     for (int i = 0; i < KV; ++i) {
-                        *reinterpret_cast<float4*>(o + i * 128) =
-                            make_float4(acc[i].x * sc, acc[i].y * sc, acc[i].z * sc, acc[i].w * sc);
+                        const float4 res = make_float4(acc[i].x * sc, acc[i].y * sc, acc[i].z * sc, acc[i].w * sc);
+                        *reinterpret_cast<float4*>(o + i * 128) = res;
                         acc[i] = f4(neutral);
                     }
                 }
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(256, 4) seg_lean_kernel(const LeanParams p) {
     }
 }
 
-template <int KV, int SMODE, bool HAS_W, bool HALO, int AGG>
+template <int KV, int SMODE, bool HAS_W, int HALO, int AGG>
 int launch_lean3(const LeanParams& p, cudaStream_t st) {
     const unsigned blocks = (unsigned)ceil_div(p.n_items, 8);
     seg_lean_kernel<KV, SMODE, HAS_W, HALO, AGG><<<blocks, 256, 0, st>>>(p);
@@ -257,14 +260,14 @@ int launch_lean3(const LeanParams& p, cudaStream_t st) {
 // instances: SUM with every scale source, with and without a halo base; MEAN and MAX/MIN for the plain messages
 // (copy_xj, w_mul_xj) — the shapes the layers use; anything else stays with seg_reduce_kernel
 template <int KV>
-int launch_lean1(const LeanParams& p, int smode, bool has_w, bool halo, int agg, cudaStream_t st) {
+int launch_lean1(const LeanParams& p, int smode, bool has_w, int halo, int agg, cudaStream_t st) {
 #define GNNB_LEAN(S, W, H, A) if (smode == S && has_w == W && halo == H && agg == A) return launch_lean3<KV, S, W, H, A>(p, st);
-    GNNB_LEAN(0, false, false, AG_SUM) GNNB_LEAN(0, true, false, AG_SUM) GNNB_LEAN(1, false, false, AG_SUM)
-    GNNB_LEAN(1, true, false, AG_SUM) GNNB_LEAN(2, false, false, AG_SUM) GNNB_LEAN(2, true, false, AG_SUM)
-    GNNB_LEAN(0, false, true, AG_SUM) GNNB_LEAN(0, true, true, AG_SUM) GNNB_LEAN(1, false, true, AG_SUM)
-    GNNB_LEAN(1, true, true, AG_SUM) GNNB_LEAN(2, false, true, AG_SUM) GNNB_LEAN(2, true, true, AG_SUM)
-    GNNB_LEAN(0, false, false, AG_MEAN) GNNB_LEAN(0, true, false, AG_MEAN)
-    GNNB_LEAN(0, false, false, AG_MAX) GNNB_LEAN(0, true, false, AG_MAX)
+    GNNB_LEAN(0, false, 0, AG_SUM) GNNB_LEAN(0, true, 0, AG_SUM) GNNB_LEAN(1, false, 0, AG_SUM)
+    GNNB_LEAN(1, true, 0, AG_SUM) GNNB_LEAN(2, false, 0, AG_SUM) GNNB_LEAN(2, true, 0, AG_SUM)
+    GNNB_LEAN(0, false, 1, AG_SUM) GNNB_LEAN(0, true, 1, AG_SUM) GNNB_LEAN(1, false, 1, AG_SUM)
+    GNNB_LEAN(1, true, 1, AG_SUM) GNNB_LEAN(2, false, 1, AG_SUM) GNNB_LEAN(2, true, 1, AG_SUM)
+    GNNB_LEAN(0, false, 0, AG_MEAN) GNNB_LEAN(0, true, 0, AG_MEAN)
+    GNNB_LEAN(0, false, 0, AG_MAX) GNNB_LEAN(0, true, 0, AG_MAX)
 #undef GNNB_LEAN
     return GNNB_EUNSUPPORTED;
 }
@@ -366,9 +369,12 @@ int seg_reduce_lean(gnnb_graph* g, const Csr& c, const SegArgs& a, float* ws, bo
     p.mean = (a.aggr == GNNB_MEAN);
     p.sign = (a.aggr == GNNB_MIN) ? -1.f : 1.f;
     if (p.n_items == 0) return GNNB_OK;
-    if (a.D == 128) return launch_lean1<1>(p, smode, a.w != nullptr, halo, agg, st);
-    if (a.D == 256) return launch_lean1<2>(p, smode, a.w != nullptr, halo, agg, st);
-    return launch_lean1<4>(p, smode, a.w != nullptr, halo, agg, st);
+    const int use_halo = halo ? 1 : 0;
+    int rc;
+    if (a.D == 128) rc = launch_lean1<1>(p, smode, a.w != nullptr, use_halo, agg, st);
+    else if (a.D == 256) rc = launch_lean1<2>(p, smode, a.w != nullptr, use_halo, agg, st);
+    else rc = launch_lean1<4>(p, smode, a.w != nullptr, use_halo, agg, st);
+    return rc;
 }
 
 }  // namespace gnnb

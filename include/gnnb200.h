@@ -310,14 +310,10 @@ int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t
  * power of two in [32, 4096]); affects plans created afterwards. */
 int gnnb_set_chunk_edges(int chunk);
 /* A/B switch for the fused segmented reduce on fp32 rows of 128/256/512 floats (results are bit-identical):
- * 0 = register-staged LDG.128 kernel, capped at 64 registers for 32 resident warps/SM (default, fastest measured);
- * 1 = TMA-staged: one cp.async.bulk (UBLKCP) per row into a shared-memory ring, mbarrier completion;
- * 2..4 = cp.async (LDGSTS) rings of 64/32/16 rows per warp;  5 = register-staged kernel without the register cap;
- * 6, 7 = the default kernel with the next group's index words (col, row, cs[col], w) prefetched under the current
- * group's row loads, 8 / 6 row loads in flight;  8, 9 = the same, reading the chunk decomposition from a 16 B-per-chunk
- * table built once per plan instead of three dependent loads per warp (6..9 were written after round 1's GPU budget:
- * unmeasured; they live in their own translation unit and leave the code of variants 0..5 untouched).
- * Measurements: profiles/r1_seg_variants.md. */
+ * 0 = default: the lean work-item kernel (csrc/seglean.cu), taking the plan's per-edge scale stream when there is one;
+ * 10 = the lean kernel gathering cs[col] per edge;  12 = seg_reduce_kernel (the round-1 default: register-staged
+ * LDG.128, 64-register cap);  5 = the same without the register cap;  1 = TMA-staged: one cp.async.bulk (UBLKCP) per
+ * row into a shared-memory ring, mbarrier completion.  Measurements: profiles/r1_seg_variants.md, profiles/r2_seg_lean.md. */
 int gnnb_set_kernel_variant(int v);
 
 #ifdef __cplusplus
