@@ -110,7 +110,17 @@ _SIGS = {
     "gnnb_sample_positions_host": (_int, [_i32, _i64, _int, C.c_uint64, C.c_uint64, _vp, _i64, C.POINTER(_i64)]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_gcn_propagate_host": (_int, [_vp, _int, _f32p, _f32p, _i64, _f32p]),
+    "gnnb_gcn_conv_step_host": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "gnnb_rmat_edges": (_int, [_i64, _i64, C.c_uint64, _vp, _vp, _vp]),
+    "gnnb_rmat_edges_range": (_int, [_i64, _i64, _i64, C.c_uint64, _vp, _vp, _vp]),
+    "gnnb_shard_builder_create": (_int, [C.POINTER(_vp), _i64, _int, _int, _int, C.POINTER(_i64), _vp]),
+    "gnnb_shard_builder_add": (_int, [_vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "gnnb_shard_builder_finish": (_int, [_vp, _int, _int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64),
+                                         C.POINTER(_i64), _vp]),
+    "gnnb_degree_accumulate": (_int, [_vp, _vp, _i64, _int, _int, _i64, _vp, _vp]),
+    "gnnb_balanced_relabel": (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
+    "gnnb_shard_builder_halo": (_int, [_vp, _int, _vp, _vp]),
+    "gnnb_shard_builder_destroy": (_int, [_vp]),
     "gnnb_set_chunk_edges": (_int, [_int]),
     "gnnb_set_kernel_variant": (_int, [_int]),
 }

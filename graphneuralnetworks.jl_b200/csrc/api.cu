@@ -33,10 +33,11 @@ __host__ __device__ static inline uint64_t splitmix64(uint64_t x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
-__global__ void rmat_kernel(int64_t N, int64_t E, uint64_t seed, int scale, int64_t* __restrict__ src,
+__global__ void rmat_kernel(int64_t N, int64_t first, int64_t count, uint64_t seed, int scale, int64_t* __restrict__ src,
                             int64_t* __restrict__ dst) {
-    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= E) return;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int64_t id = first + k;                    // the edge's global counter: a chunk equals the same slice of the whole list
     const uint32_t TA = 9563013u, TB = 12750684u, TC = 15938355u;  // floor(.57, .76, .95 * 2^24)
     uint64_t s = 0, d = 0;
     for (uint64_t retry = 0;; ++retry) {
@@ -53,8 +54,8 @@ __global__ void rmat_kernel(int64_t N, int64_t E, uint64_t seed, int scale, int6
         if ((int64_t)s < N && (int64_t)d < N) break;
         if (retry >= 63) { s %= (uint64_t)N; d %= (uint64_t)N; break; }
     }
-    src[id] = (int64_t)s + 1;
-    dst[id] = (int64_t)d + 1;
+    src[k] = (int64_t)s + 1;
+    dst[k] = (int64_t)d + 1;
 }
 
 }  // namespace gnnb
@@ -247,17 +248,101 @@ int gnnb_gcn_propagate_host(gnnb_graph_t g, int transposed, const float* x_host,
     return host_pass(g, transposed, GNNB_COPY_XJ, GNNB_SUM, 1, x_host, w_host, D, out_host);
 }
 
-int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t* src_dev, int64_t* dst_dev,
-                    void* stream) {
-    if (num_nodes <= 0 || num_edges < 0) GNNB_FAIL(GNNB_ESIZE, "rmat: bad sizes");
-    if (!src_dev || !dst_dev) GNNB_FAIL(GNNB_EINVAL, "rmat: NULL output");
+// ---- one GCNConv forward + backward on host arrays ----------------------------------------------------------------
+int gnnb_gcn_conv_step_host(gnnb_graph_t g, const float* x_host, const float* W_host, const float* b_host, int relu,
+                            int64_t Din, int64_t Dout, const float* dy_host, float* y_host, float* dx_host,
+                            float* dW_host, float* db_host) {
+    if (!g) GNNB_FAIL(GNNB_EINVAL, "graph handle is NULL");
+    if (g->n_src != g->n_dst) GNNB_FAIL(GNNB_ESIZE, "gcn_conv needs num_src == num_dst");
+    if (Din <= 0 || Dout <= 0) GNNB_FAIL(GNNB_ESIZE, "feature dimensions must be positive");
+    if (!x_host || !W_host || !y_host) GNNB_FAIL(GNNB_EINVAL, "host buffer is NULL");
+    const bool bwd = dy_host != nullptr;
+    if (bwd && (!dx_host || !dW_host)) GNNB_FAIL(GNNB_EINVAL, "the backward half needs dx_host and dW_host");
+    const int64_t N = g->n_dst;
+    if (Dout < Din)                                        // conv.jl:36-40 multiplies before the convolution then
+        GNNB_FAIL(GNNB_EUNSUPPORTED, "gcn_conv_step_host serves the Dout >= Din branch (propagate, then GEMM with bias/activation)");
+    const int64_t Dp = Din;                                // width at which the graph is traversed
+    // device staging, carved from one plan-owned allocation: x, p (propagated / pre-propagated), y, dy, dpre, dp, dx, W, b, dW, db
+    const size_t nx = (size_t)N * Din, np_ = (size_t)N * Dp, ny = (size_t)N * Dout;
+    const size_t words = nx + np_ + ny + (bwd ? (ny + ny + np_ + nx) : 0) + 2 * (size_t)(Dout * Din) + 2 * (size_t)Dout + 64;
+    if (g->host_ws_bytes < words * sizeof(float)) {
+        if (g->host_ws) { cudaDeviceSynchronize(); cudaFree(g->host_ws); g->host_ws = nullptr; g->host_ws_bytes = 0; }
+        GNNB_CUDA(cudaMalloc(&g->host_ws, words * sizeof(float)));
+        g->host_ws_bytes = words * sizeof(float);
+    }
+    float* q = (float*)g->host_ws;
+    auto take = [&](size_t n) { float* r = q; q += (n + 3) & ~(size_t)3; return r; };
+    float *x = take(nx), *p = take(np_), *y = take(ny);
+    float *dy = bwd ? take(ny) : nullptr, *dpre = bwd ? take(ny) : nullptr, *dp = bwd ? take(np_) : nullptr, *dx = bwd ? take(nx) : nullptr;
+    float *W = take((size_t)(Dout * Din)), *b = take((size_t)Dout), *dW = take((size_t)(Dout * Din)), *db = take((size_t)Dout);
+    cudaStream_t s_main = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_x = nullptr, ev_dy = nullptr, ev_y = nullptr, ev_dx = nullptr;
+    int status = GNNB_OK;
+#define HP(expr) { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s: %s", #expr, cudaGetErrorString(_e)); status = GNNB_ECUDA; goto done; } }
+#define HT(expr) { status = (expr); if (status != GNNB_OK) goto done; }
+    HP(cudaStreamCreateWithFlags(&s_main, cudaStreamNonBlocking));
+    HP(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    HP(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    HP(cudaEventCreateWithFlags(&ev_x, cudaEventDisableTiming));
+    HP(cudaEventCreateWithFlags(&ev_dy, cudaEventDisableTiming));
+    HP(cudaEventCreateWithFlags(&ev_y, cudaEventDisableTiming));
+    HP(cudaEventCreateWithFlags(&ev_dx, cudaEventDisableTiming));
+    // uploads ride s_in, downloads s_out (PCIe is full duplex), kernels s_main
+    HP(cudaMemcpyAsync(W, W_host, sizeof(float) * (size_t)(Dout * Din), cudaMemcpyHostToDevice, s_in));
+    if (b_host) HP(cudaMemcpyAsync(b, b_host, sizeof(float) * (size_t)Dout, cudaMemcpyHostToDevice, s_in));
+    HP(cudaMemcpyAsync(x, x_host, sizeof(float) * nx, cudaMemcpyHostToDevice, s_in));
+    HP(cudaEventRecord(ev_x, s_in));
+    if (bwd) {
+        HP(cudaMemcpyAsync(dy, dy_host, sizeof(float) * ny, cudaMemcpyHostToDevice, s_in));
+        HP(cudaEventRecord(ev_dy, s_in));
+    }
+    HP(cudaStreamWaitEvent(s_main, ev_x, 0));
+    HT(gnnb_gcn_propagate(g, 0, x, nullptr, nullptr, Dp, p, s_main));                     // p = Â x
+    HT(gnnb_linear(p, W, b_host ? b : nullptr, relu, N, Din, Dout, y, s_main));           // y = act(W p + b)
+    HP(cudaEventRecord(ev_y, s_main));
+    HP(cudaStreamWaitEvent(s_out, ev_y, 0));
+    HP(cudaMemcpyAsync(y_host, y, sizeof(float) * ny, cudaMemcpyDeviceToHost, s_out));
+    if (bwd) {
+        HP(cudaStreamWaitEvent(s_main, ev_dy, 0));
+        HT(gnnb_linear_bwd(dy, y, p, W, relu, N, Din, Dout, dpre, dp, dW, (b_host && db_host) ? db : nullptr, s_main));
+        HT(gnnb_gcn_propagate(g, 1, dp, nullptr, nullptr, Dp, dx, s_main));               // dx = Â' dp
+        HP(cudaEventRecord(ev_dx, s_main));
+        HP(cudaStreamWaitEvent(s_out, ev_dx, 0));
+        HP(cudaMemcpyAsync(dx_host, dx, sizeof(float) * nx, cudaMemcpyDeviceToHost, s_out));
+        HP(cudaMemcpyAsync(dW_host, dW, sizeof(float) * (size_t)(Dout * Din), cudaMemcpyDeviceToHost, s_out));
+        if (b_host && db_host) HP(cudaMemcpyAsync(db_host, db, sizeof(float) * (size_t)Dout, cudaMemcpyDeviceToHost, s_out));
+    }
+    HP(cudaStreamSynchronize(s_out));
+    HP(cudaStreamSynchronize(s_main));
+#undef HP
+#undef HT
+done:
+    if (status != GNNB_OK) cudaDeviceSynchronize();
+    if (ev_x) cudaEventDestroy(ev_x);
+    if (ev_dy) cudaEventDestroy(ev_dy);
+    if (ev_y) cudaEventDestroy(ev_y);
+    if (ev_dx) cudaEventDestroy(ev_dx);
+    if (s_main) cudaStreamDestroy(s_main);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    return status;
+}
+
+int gnnb_rmat_edges_range(int64_t num_nodes, int64_t first_edge, int64_t count, uint64_t seed, int64_t* src_dev,
+                          int64_t* dst_dev, void* stream) {
+    if (num_nodes <= 0 || count < 0 || first_edge < 0) GNNB_FAIL(GNNB_ESIZE, "rmat: bad sizes");
+    if (count > 0 && (!src_dev || !dst_dev)) GNNB_FAIL(GNNB_EINVAL, "rmat: NULL output");
     if (gnnb_device_count() <= 0) GNNB_FAIL(GNNB_ECUDA, "no CUDA device");
     int scale = 0;
     while (((int64_t)1 << scale) < num_nodes) ++scale;
-    if (num_edges == 0) return GNNB_OK;
-    rmat_kernel<<<nblk(num_edges), 256, 0, (cudaStream_t)stream>>>(num_nodes, num_edges, seed, scale, src_dev, dst_dev);
+    if (count == 0) return GNNB_OK;
+    rmat_kernel<<<nblk(count), 256, 0, (cudaStream_t)stream>>>(num_nodes, first_edge, count, seed, scale, src_dev, dst_dev);
     GNNB_LAUNCHED();
     return GNNB_OK;
+}
+int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t* src_dev, int64_t* dst_dev,
+                    void* stream) {
+    return gnnb_rmat_edges_range(num_nodes, 0, num_edges, seed, src_dev, dst_dev, stream);
 }
 
 }  // extern "C"

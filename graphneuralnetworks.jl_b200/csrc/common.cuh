@@ -82,6 +82,8 @@ struct gnnb_graph {
     float* ws2 = nullptr;
     size_t ws2_bytes = 0;
     float* gcn_c = nullptr;      // lazily: 1/sqrt(in-degree), the default symmetric normalisation (unweighted), plan-owned
+    void* host_ws = nullptr;     // device staging of the *_host entries (grown on demand, freed with the plan)
+    size_t host_ws_bytes = 0;
     std::mutex mu;
 };
 

@@ -17,20 +17,24 @@ struct PushParams {
     int world;
 };
 
+// one warp per row: the lanes copy the row as float4 (or float) pieces; the destination is a peer's halo buffer
 template <int VEC>
-__global__ void halo_push_kernel(const PushParams pp, const int32_t* __restrict__ send_idx, int64_t n_send,
-                                 const float* __restrict__ x, int64_t D) {
-    const int64_t nvec = D / VEC;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_send * nvec) return;
-    const int64_t v = i / nvec, f = (i - v * nvec) * VEC;
-    const int64_t r = (int64_t)(((unsigned __int128)v * (unsigned __int128)pp.stride) % (unsigned __int128)n_send);
+__global__ void __launch_bounds__(256) halo_push_kernel(const PushParams pp, const int32_t* __restrict__ send_idx, int64_t n_send,
+                                                        const float* __restrict__ x, int64_t D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (v >= n_send) return;
+    const int64_t r = (int64_t)(((uint64_t)v * (uint64_t)pp.stride) % (uint64_t)n_send);   // stride < 2^25, v < 2^31
     int p = 0;
     while (p + 1 < pp.world && r >= pp.seg_start[p + 1]) ++p;       // <= 16 peers: a short scan
-    float* dst = pp.peer_base[p] + (size_t)(pp.peer_row0[p] + (r - pp.seg_start[p])) * D + f;
-    const float* src = x + (size_t)send_idx[r] * D + f;
-    if (VEC == 4) *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
-    else *dst = __ldg(src);
+    float* dst = pp.peer_base[p] + (size_t)(pp.peer_row0[p] + (r - pp.seg_start[p])) * D;
+    const float* src = x + (size_t)__ldg(send_idx + r) * D;
+    if (VEC == 4) {
+        for (int64_t f = (int64_t)lane * 4; f < D; f += 128)
+            *reinterpret_cast<float4*>(dst + f) = __ldg(reinterpret_cast<const float4*>(src + f));
+    } else {
+        for (int64_t f = lane; f < D; f += 32) dst[f] = __ldg(src + f);
+    }
 }
 
 }  // namespace gnnb
@@ -96,8 +100,8 @@ int gnnb_halo_push(const int32_t* send_idx_dev, const int64_t* seg_start_host, c
     cudaStream_t st = (cudaStream_t)stream;
     bool v4 = D % 4 == 0 && !((uintptr_t)x & 15);
     for (int p = 0; p < world; ++p) if ((uintptr_t)pp.peer_base[p] & 15) v4 = false;
-    if (v4) halo_push_kernel<4><<<(unsigned)ceil_div(n_send * (D / 4), 256), 256, 0, st>>>(pp, send_idx_dev, n_send, x, D);
-    else halo_push_kernel<1><<<(unsigned)ceil_div(n_send * D, 256), 256, 0, st>>>(pp, send_idx_dev, n_send, x, D);
+    if (v4) halo_push_kernel<4><<<(unsigned)ceil_div(n_send, 8), 256, 0, st>>>(pp, send_idx_dev, n_send, x, D);
+    else halo_push_kernel<1><<<(unsigned)ceil_div(n_send, 8), 256, 0, st>>>(pp, send_idx_dev, n_send, x, D);
     GNNB_LAUNCHED();
     return GNNB_OK;
 }

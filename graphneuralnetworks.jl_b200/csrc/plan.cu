@@ -285,6 +285,7 @@ int gnnb_graph_destroy(gnnb_graph_t g) {
     cudaFree(g->ws);
     cudaFree(g->ws2);
     cudaFree(g->gcn_c);
+    cudaFree(g->host_ws);
     delete g;
     return GNNB_OK;
 }

@@ -31,13 +31,6 @@ from . import _lib
 from ._lib import lib
 from .graph import _Plan, _ptr, _stream, rows, unrows
 
-def overlap_enabled() -> bool:
-    """GNNB_OVERLAP=1: run the halo exchange on a side stream under the part of the reduction that only needs local
-    rows (opt-in; sums a row's local and halo contributions separately, so the result is no longer bit-identical to
-    the single-GPU summation order — within the fp32 tolerance instead)."""
-    return os.environ.get("GNNB_OVERLAP", "0") == "1"
-
-
 NODE_COST = 12  # dense per-node work (GEMM, bias, relu, grads) in edge-equivalents, from the 1-GPU profile (1.9 ns/node vs 0.17 ns/edge)
 
 
@@ -57,12 +50,46 @@ def balanced_bounds(cost: torch.Tensor, world: int) -> List[int]:
     return b
 
 
+def ownership_first(num_nodes: int, world: int, ownership: str, bounds: Optional[List[int]] = None) -> List[int]:
+    """Start of every rank's range in partition-id space (world + 1 entries).  'contiguous': the node ranges themselves
+    (`bounds`, or equal ranges); 'cyclic': node v (0-based) belongs to rank v % world as local row v // world, so rank q
+    owns ceil((N - q) / world) nodes — the hubs of a skewed id space (RMAT: the low ids) spread over all ranks."""
+    if ownership == "contiguous":
+        return list(bounds) if bounds is not None else [(num_nodes * q) // world for q in range(world + 1)]
+    assert ownership in ("cyclic", "balanced"), ownership
+    first = [0]
+    for q in range(world):
+        first.append(first[-1] + (num_nodes - q + world - 1) // world)
+    return first
+
+
+def to_pid(v0: torch.Tensor, world: int, first: List[int], ownership: str, relabel: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """node id (0-based) -> partition id: the bijection onto [0, N) in which every rank owns one contiguous range"""
+    if ownership == "contiguous":
+        return v0
+    if relabel is not None:
+        v0 = relabel.to(v0.dtype)[v0]
+    ft = torch.tensor(first[:-1], dtype=v0.dtype, device=v0.device)
+    return ft[v0 % world] + v0 // world
+
+
+def degree_order(chunks, num_nodes: int, device) -> torch.Tensor:
+    """nodes by decreasing in+out degree (stable: ties keep id order) — the order in which 'balanced' ownership deals
+    them to the ranks; the torch restatement of gnnb_degree_accumulate + the sort of gnnb_balanced_relabel."""
+    cost = torch.zeros(num_nodes, dtype=torch.int64, device=device)
+    for sc, tc in chunks:
+        cost += torch.bincount(sc.to(device).to(torch.int64) - 1, minlength=num_nodes)
+        cost += torch.bincount(tc.to(device).to(torch.int64) - 1, minlength=num_nodes)
+    return torch.sort(cost, descending=True, stable=True).indices
+
+
 def build_shard(key0: torch.Tensor, other0: torch.Tensor, lo: int, hi: int, bounds: List[int],
                 self_loops: bool):
-    """Edges whose reduction row `key0` (0-based global) lies in [lo,hi), re-indexed for one GPU.
+    """Edges whose reduction row `key0` (0-based partition id) lies in [lo,hi), re-indexed for one GPU — the torch
+    restatement of csrc/shard.cu, used for CPU tensors (gloo tests of the host logic).
 
-    Returns dict(row: local reduction row, col: gathered node in [local | halo] space, halo: sorted global ids of
-    the remote gathered nodes, recv_counts: rows expected from every owner)."""
+    Returns dict(row: local reduction row, col: gathered node in [local | halo] space, halo: sorted partition ids of
+    the remote gathered nodes, halo_local: their owner-local rows, recv_counts: rows expected from every owner)."""
     sel = (key0 >= lo) & (key0 < hi)
     k = key0[sel] - lo
     o = other0[sel]
@@ -77,91 +104,201 @@ def build_shard(key0: torch.Tensor, other0: torch.Tensor, lo: int, hi: int, boun
     edges = torch.tensor(bounds[1:], dtype=halo.dtype, device=halo.device)
     owner = torch.bucketize(halo, edges, right=True)
     recv_counts = torch.bincount(owner, minlength=len(bounds) - 1).tolist()
-    return {"row": k, "col": col, "halo": halo, "recv_counts": recv_counts, "n_local": n_local}
+    starts = torch.tensor(bounds[:-1], dtype=halo.dtype, device=halo.device)
+    halo_local = (halo - starts[owner]).to(torch.int32)
+    return {"row": k, "col": col, "halo": halo, "halo_local": halo_local, "recv_counts": recv_counts, "n_local": n_local}
 
 
-def exchange_requests(halo: torch.Tensor, recv_counts: List[int], lo: int, group=None):
-    """Tell every owner which of its rows this rank needs.  Returns (send_idx int32 local row ids to pack, in peer
-    order; send_counts)."""
-    world = dist.get_world_size(group)
-    dev = halo.device
+def exchange_requests(halo_local: torch.Tensor, recv_counts: List[int], group=None):
+    """Tell every owner which of its rows (owner-local int32 indices, grouped by owner) this rank needs.  Returns
+    (send_idx: int32 local row ids to pack, in peer order; send_counts)."""
+    dev = halo_local.device
     rc = torch.tensor(recv_counts, dtype=torch.int64, device=dev)
     sc = torch.empty_like(rc)
     dist.all_to_all_single(sc, rc, group=group)
     send_counts = sc.tolist()
-    wanted = torch.empty(int(sum(send_counts)), dtype=torch.int64, device=dev)
-    dist.all_to_all_single(wanted, halo.to(torch.int64).contiguous(), output_split_sizes=send_counts,
+    wanted = torch.empty(int(sum(send_counts)), dtype=torch.int32, device=dev)
+    dist.all_to_all_single(wanted, halo_local.to(torch.int32).contiguous(), output_split_sizes=send_counts,
                            input_split_sizes=recv_counts, group=group)
-    send_idx = (wanted - lo).to(torch.int32)
-    return send_idx, send_counts
+    return wanted, send_counts
 
 
 # ---------------------------------------------------------------------------------------------------------
 # the distributed graph
 # ---------------------------------------------------------------------------------------------------------
 class _Shard:
-    def __init__(self, d, send_idx, send_counts, plan, split=None):
-        self.split = split         # (plan over the edges with a local source, plan over the edges with a halo source)
-        self.n_local = d["n_local"]
-        self.n_halo = int(d["halo"].numel())
-        self.recv_counts = d["recv_counts"]
+    def __init__(self, n_local, n_halo, recv_counts, num_edges, send_idx, send_counts, plan):
+        self.n_local = int(n_local)
+        self.n_halo = int(n_halo)
+        self.recv_counts = [int(v) for v in recv_counts]
         self.send_idx = send_idx
         self.send_counts = send_counts
         self.plan = plan
-        self.num_edges = int(d["row"].numel())
+        self.num_edges = int(num_edges)
         self.push = None           # per-D state of the peer-to-peer push path (_PushState)
 
 
 class DistGraph:
-    """A GNNGraph partitioned over the ranks of `group`.  Every rank passes the same global COO (1-based s, t)."""
+    """A GNNGraph partitioned over the ranks of `group`.
 
-    def __init__(self, s: torch.Tensor, t: torch.Tensor, num_nodes: int, *, add_self_loops: bool = False,
-                 group=None, device=None, bounds: Optional[List[int]] = None):
+    DistGraph(s, t, num_nodes, ...): every rank passes the same global COO (1-based s, t).
+    DistGraph.from_chunks(chunks, num_nodes, ...): the same from an iterable of (s, t) chunks — the global list is never
+    resident (CUDA only).  DistGraph.from_rmat(...) generates the chunks of the counter-based RMAT list on the device.
+    On a CUDA device the shards are built by csrc/shard.cu (stable scan-compaction of every chunk, sort + unique of the
+    remote ids, renaming, plan); on CPU tensors (gloo tests) by the torch restatement above.
+
+    ownership = 'contiguous' (node ranges, cost-balanced unless `bounds` is given), 'cyclic' (0-based node v on rank
+    v % world) or 'balanced' (nodes sorted by decreasing degree and dealt to the ranks in turn: edges, nodes and served
+    halo rows all balanced whatever the id space looks like — RMAT probabilities are products over id bits, so neither
+    ranges nor v % world balance it; needs `chunks` to be iterable twice).  `local_nodes()` lists the owned node ids in
+    local-row order."""
+
+    def __init__(self, s: Optional[torch.Tensor], t: Optional[torch.Tensor], num_nodes: int, *, add_self_loops: bool = False,
+                 group=None, device=None, bounds: Optional[List[int]] = None, ownership: str = "contiguous",
+                 chunks=None, chunk_edges: int = 1 << 26):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device(device) if device is not None else s.device
         self.num_nodes = int(num_nodes)
-        s0 = s.to(self.device).to(torch.int64) - 1
-        t0 = t.to(self.device).to(torch.int64) - 1
-        if bounds is None:
-            cost = (torch.bincount(t0, minlength=num_nodes) + torch.bincount(s0, minlength=num_nodes) + NODE_COST)
-            bounds = balanced_bounds(cost, self.world)
-        self.bounds = bounds
-        self.lo, self.hi = bounds[self.rank], bounds[self.rank + 1]
-        self.n_local = self.hi - self.lo
+        self.ownership = ownership
         self.self_loops = add_self_loops
-        self.fwd = self._make(t0, s0, add_self_loops)      # reduce over in-edges of owned targets, gather sources
-        self.bwd = self._make(s0, t0, add_self_loops)      # reduce over out-edges of owned sources, gather targets
         self._c = None
-
-    def _make(self, key0, other0, loops) -> _Shard:
-        d = build_shard(key0, other0, self.lo, self.hi, self.bounds, loops)
-        send_idx, send_counts = exchange_requests(d["halo"], d["recv_counts"], self.lo, self.group)
-        plan, split = None, None
+        if chunks is None:
+            s = s.to(self.device)
+            t = t.to(self.device)
+            if ownership == "contiguous" and bounds is None:
+                s0, t0 = s.to(torch.int64) - 1, t.to(torch.int64) - 1
+                cost = (torch.bincount(t0, minlength=num_nodes) + torch.bincount(s0, minlength=num_nodes) + NODE_COST)
+                bounds = balanced_bounds(cost, self.world)
+                del s0, t0, cost
+            E = int(s.numel())
+            chunks = [(s[i:i + chunk_edges], t[i:i + chunk_edges]) for i in range(0, max(E, 1), chunk_edges)] if E else []
+        self._order = self._relabel = None
+        if ownership == "balanced":
+            if not isinstance(chunks, (list, tuple)) and not callable(chunks):
+                raise ValueError("ownership='balanced' needs the chunks twice: pass a list or a callable that returns an iterator")
+            W, N = self.world, self.num_nodes
+            it = chunks() if callable(chunks) else chunks
+            if self.device.type == "cuda":                   # degree histogram + stable sort + deal, on the device
+                cost = torch.zeros(N, dtype=torch.int32, device=self.device)
+                self._relabel = torch.empty(N, dtype=torch.int32, device=self.device)
+                order = torch.empty(N, dtype=torch.int32, device=self.device)
+                with torch.cuda.device(self.device):
+                    for sc, tc in it:
+                        sc, tc = sc.to(self.device).contiguous(), tc.to(self.device).contiguous()
+                        _lib.check(lib.gnnb_degree_accumulate(sc.data_ptr(), tc.data_ptr(), sc.numel(), sc.element_size(), 1, N,
+                                                              cost.data_ptr(), _stream(self.device)))
+                    _lib.check(lib.gnnb_balanced_relabel(cost.data_ptr(), N, W, self._relabel.data_ptr(), order.data_ptr(),
+                                                         _stream(self.device)))
+                self._order = order
+                del cost
+            else:                                            # the same deal in torch ops (gloo tests)
+                by_degree = degree_order(it, N, self.device)
+                pos = torch.arange(N, device=self.device)
+                r, j = pos // W, pos % W
+                o = torch.where((r % 2 == 1) & (r < N // W), W - 1 - j, j)
+                self._relabel = torch.empty(N, dtype=torch.int32, device=self.device)
+                self._relabel[by_degree] = (r * W + o).to(torch.int32)
+                self._order = torch.empty(N, dtype=torch.int64, device=self.device)      # position -> node
+                self._order[self._relabel.long()] = pos
+                del by_degree, pos, r, j, o
+        if callable(chunks):
+            chunks = chunks()
+        self.first = ownership_first(self.num_nodes, self.world, ownership, bounds)
+        self.bounds = self.first
+        self.lo, self.hi = self.first[self.rank], self.first[self.rank + 1]
+        self.n_local = self.hi - self.lo
         if self.device.type == "cuda":
-            plan, split = self._plans(d)
-        return _Shard(d, send_idx, send_counts, plan, split)
+            self.fwd, self.bwd = self._build_native(chunks)
+        else:
+            self.fwd, self.bwd = self._build_torch(chunks)
+
+    @classmethod
+    def from_chunks(cls, chunks, num_nodes: int, **kw):
+        return cls(None, None, num_nodes, chunks=chunks, **kw)
+
+    @classmethod
+    def from_rmat(cls, num_nodes: int, num_edges: int, seed: int = 17, *, device, chunk_edges: int = 1 << 26, **kw):
+        """the RMAT list of gnnb_rmat_edges, generated (identically on every rank) and consumed chunk by chunk"""
+        dev = torch.device(device)
+
+        buf = [torch.empty(min(chunk_edges, max(num_edges, 1)), dtype=torch.int64, device=dev) for _ in range(2)]
+
+        def gen():
+            s, t = buf
+            for first in range(0, num_edges, chunk_edges):
+                cnt = min(chunk_edges, num_edges - first)
+                with torch.cuda.device(dev):
+                    _lib.check(lib.gnnb_rmat_edges_range(num_nodes, first, cnt, seed, s.data_ptr(), t.data_ptr(), _stream(dev)))
+                yield s[:cnt], t[:cnt]
+
+        return cls(None, None, num_nodes, chunks=gen, device=dev, **kw)
+
+    def local_nodes(self) -> torch.Tensor:
+        """0-based global node id of every local row, in local-row order"""
+        if self.ownership == "contiguous":
+            return torch.arange(self.lo, self.hi, device=self.device)
+        pos = self.rank + self.world * torch.arange(self.n_local, device=self.device)
+        return pos if self._order is None else self._order[pos].long()
+
+    # -- shard construction on the device (csrc/shard.cu)
+    def _build_native(self, chunks):
+        dev, world = self.device, self.world
+        b = C.c_void_p()
+        bounds_arr = (C.c_int64 * (world + 1))(*self.first) if self.ownership == "contiguous" else None
+        shards = []
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            _lib.check(lib.gnnb_shard_builder_create(C.byref(b), self.num_nodes, world, self.rank,
+                                                     0 if self.ownership == "contiguous" else 1, bounds_arr,
+                                                     None if self._relabel is None else self._relabel.data_ptr()))
+            try:
+                for sc, tc in chunks:
+                    sc, tc = sc.to(dev).contiguous(), tc.to(dev).contiguous()
+                    assert sc.dtype == tc.dtype and sc.dtype in (torch.int32, torch.int64)
+                    _lib.check(lib.gnnb_shard_builder_add(b, sc.data_ptr(), tc.data_ptr(), sc.numel(), sc.element_size(), 1, st))
+                for direction in (0, 1):
+                    h = C.c_void_p()
+                    nl, nh, ne = C.c_int64(), C.c_int64(), C.c_int64()
+                    rc = (C.c_int64 * world)()
+                    _lib.check(lib.gnnb_shard_builder_finish(b, direction, int(self.self_loops), C.byref(h), C.byref(nl),
+                                                             C.byref(nh), C.byref(ne), rc, st))
+                    halo_local = torch.empty(max(nh.value, 1), dtype=torch.int32, device=dev)[:nh.value]
+                    _lib.check(lib.gnnb_shard_builder_halo(b, direction, halo_local.data_ptr() if nh.value else None, st))
+                    shards.append((h, nl.value, nh.value, ne.value, list(rc), halo_local))
+            finally:
+                lib.gnnb_shard_builder_destroy(b)
+        out = []
+        for h, nl, nh, ne, rc, halo_local in shards:
+            send_idx, send_counts = exchange_requests(halo_local, rc, self.group)
+            out.append(_Shard(nl, nh, rc, ne, send_idx, send_counts, _Plan(h.value, dev)))
+        return out
 
     def _plans(self, d):
-        """the shard's plan over [local | halo] sources and, for the overlapped schedule (GNNB_OVERLAP=1), the same
-        edges split by where the source lives: (local sources -> targets), (halo sources -> targets)."""
-        def make(col, row, n_src):
-            h = C.c_void_p()
-            col, row = col.to(torch.int32).contiguous(), row.to(torch.int32).contiguous()
-            with torch.cuda.device(self.device):
-                _lib.check(lib.gnnb_graph_create(C.byref(h), col.data_ptr(), row.data_ptr(), row.numel(), n_src,
-                                                 d["n_local"], 4, 0, 1, _stream(self.device)))
-            return _Plan(h.value, self.device)
+        """plan of a torch-built shard dict over [local | halo] sources (the gloo tests call this with the CPU test double
+        installed)"""
+        h = C.c_void_p()
+        col, row = d["col"].to(torch.int32).contiguous(), d["row"].to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.gnnb_graph_create(C.byref(h), col.data_ptr(), row.data_ptr(), row.numel(),
+                                             d["n_local"] + int(d["halo"].numel()), d["n_local"], 4, 0, 1, _stream(self.device)))
+        return _Plan(h.value, self.device)
 
-        n_local, n_halo = d["n_local"], int(d["halo"].numel())
-        plan = make(d["col"], d["row"], n_local + n_halo)
-        split = None
-        if overlap_enabled() and self.world > 1:
-            loc = d["col"] < n_local
-            split = (make(d["col"][loc], d["row"][loc], n_local),
-                     make(d["col"][~loc] - n_local, d["row"][~loc], max(n_halo, 1)) if n_halo else None)
-        return plan, split
+    # -- the same in torch ops, for CPU tensors (host logic under gloo)
+    def _build_torch(self, chunks):
+        chunks = list(chunks)
+        s0 = torch.cat([c[0] for c in chunks]).to(self.device).to(torch.int64) - 1 if chunks else torch.zeros(0, dtype=torch.int64)
+        t0 = torch.cat([c[1] for c in chunks]).to(self.device).to(torch.int64) - 1 if chunks else torch.zeros(0, dtype=torch.int64)
+        ps = to_pid(s0, self.world, self.first, self.ownership, self._relabel)
+        pt = to_pid(t0, self.world, self.first, self.ownership, self._relabel)
+        out = []
+        for key0, other0 in ((pt, ps), (ps, pt)):
+            d = build_shard(key0, other0, self.lo, self.hi, self.first, self.self_loops)
+            send_idx, send_counts = exchange_requests(d["halo_local"], d["recv_counts"], self.group)
+            out.append(_Shard(d["n_local"], d["halo"].numel(), d["recv_counts"], d["row"].numel(), send_idx, send_counts,
+                              None))
+        return out
 
     # -- halo exchange: rows (n_local, D) -> halo rows (n_halo, D)
     def halo(self, shard: _Shard, x_rows: torch.Tensor) -> torch.Tensor:
@@ -223,7 +360,8 @@ class DistGraph:
             ok = 0
         flag = torch.tensor([ok], device=dev, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        if int(flag.item()) == 0:
+        if int(flag.item()) == 0:                               # NCCL for everyone: give back what this rank did set up
+            self._release_push({"bufs": bufs, "peer_ptrs": peer_ptrs})
             shard.push[D] = None
             return None
         seg = [0]
@@ -231,9 +369,38 @@ class DistGraph:
             seg.append(seg[-1] + int(shard.send_counts[q]))
         st = {"bufs": bufs, "row0": (C.c_int64 * world)(*row0), "seg": (C.c_int64 * (world + 1))(*seg),
               "peer_c": [(C.c_void_p * world)(*[C.c_void_p(v) for v in peer_ptrs[b]]) for b in range(2)], "turn": 0,
+              "peer_ptrs": peer_ptrs,
               "flag": torch.zeros(1, device=dev)}
         shard.push[D] = st
         return st
+
+    def _release_push(self, st) -> None:
+        with torch.cuda.device(self.device):
+            for per_buf in st["peer_ptrs"]:
+                for pp in per_buf:
+                    if pp:
+                        lib.gnnb_ipc_close_handle(C.c_void_p(pp))
+            for ptr in st["bufs"]:
+                if ptr:
+                    lib.gnnb_dev_free(C.c_void_p(ptr))
+
+    def close(self) -> None:
+        """unmap the peers' halo buffers and free this rank's (call on every rank once no pass is in flight)"""
+        for sh in (getattr(self, "fwd", None), getattr(self, "bwd", None)):
+            if sh is None or not sh.push:
+                continue
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            for st in sh.push.values():
+                if st is not None:
+                    self._release_push(st)
+            sh.push = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def halo_ptr(self, shard: _Shard, x_rows: torch.Tensor) -> int:
         """device pointer of this rank's halo rows for `x_rows` (valid until the next-but-one call for this shard)"""
@@ -268,39 +435,6 @@ class DistGraph:
             self._c = (c, cf.contiguous(), cb.contiguous())
         return self._c
 
-    def _propagate_overlapped(self, shard: _Shard, x_rows: torch.Tensor, cs, ct) -> torch.Tensor:
-        """out = ct .* (A_local (cs_l .* x_local) + A_halo (cs_h .* x_halo)): the exchange runs on a side stream while
-        the main stream reduces the edges whose sources are local; SUM only."""
-        D = x_rows.shape[1]
-        dev = self.device
-        p_loc, p_hal = shard.split
-        n_local = shard.n_local
-        cs_l = None if cs is None else cs[:n_local]
-        cs_h = None if cs is None else cs[n_local:]
-        out = torch.empty_like(x_rows)
-        on_gpu = dev.type == "cuda"
-        if on_gpu:
-            main = torch.cuda.current_stream(dev)
-            if getattr(self, "_side", None) is None:
-                self._side = torch.cuda.Stream(dev)
-            self._side.wait_stream(main)                      # x_rows is complete before the push reads it
-            with torch.cuda.stream(self._side):
-                hptr = self.halo_ptr(shard, x_rows)
-        else:
-            hptr = self.halo_ptr(shard, x_rows)
-        with torch.cuda.device(dev):
-            _lib.check(lib.gnnb_propagate(p_loc.h, 0, _lib.COPY_XJ, _lib.SUM, x_rows.data_ptr(), None, _ptr(cs_l),
-                                          _ptr(ct), D, out.data_ptr(), _stream(dev)))
-        if p_hal is None:
-            return out
-        if on_gpu:
-            main.wait_stream(self._side)                      # every peer's rows have landed
-        part = torch.empty_like(x_rows)
-        with torch.cuda.device(dev):
-            _lib.check(lib.gnnb_propagate(p_hal.h, 0, _lib.COPY_XJ, _lib.SUM, hptr, None, _ptr(cs_h), _ptr(ct), D,
-                                          part.data_ptr(), _stream(dev)))
-        return out.add_(part)
-
     def propagate(self, shard: _Shard, x_rows: torch.Tensor, cs, ct, aggr=_lib.SUM) -> torch.Tensor:
         slices = int(os.environ.get("GNNB_HALO_SLICES", "1"))
         if slices > 1 and x_rows.shape[1] % slices == 0 and not getattr(self, "_slicing", False):
@@ -316,8 +450,6 @@ class DistGraph:
             finally:
                 self._slicing = False
             return out
-        if shard.split is not None and aggr == _lib.SUM:
-            return self._propagate_overlapped(shard, x_rows, cs, ct)
         D = x_rows.shape[1]
         hptr = self.halo_ptr(shard, x_rows)
         out = torch.empty_like(x_rows)
@@ -363,17 +495,19 @@ def dist_gcn_conv(l, dg: DistGraph, x_local: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------
 # bench.py --gpus N>1
 # ---------------------------------------------------------------------------------------------------------
-def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks):
+def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_leg=None):
     import gnnb200 as gnn
     n, E, D = args.nodes, args.edges, args.dim
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    g = gnn.rmat_graph(n, E, seed, device=dev)          # every rank generates the same counter-based edge list
-    dg = DistGraph(g.s, g.t, n, add_self_loops=True, device=dev)
+    # every rank generates the counter-based edge list chunk by chunk and keeps its shard (csrc/shard.cu); 'balanced'
+    # ownership deals the nodes to the ranks by decreasing degree (one extra pass over the generated chunks)
+    ownership = os.environ.get("GNNB_OWNERSHIP", "balanced")
+    dg = DistGraph.from_rmat(n, E, seed, device=dev, add_self_loops=True, ownership=ownership,
+                             chunk_edges=int(os.environ.get("GNNB_CHUNK_EDGES", str(1 << 26))))
     dg.gcn_c()
     torch.cuda.synchronize()
     t_plan = time.perf_counter() - t0
-    del g
     torch.cuda.empty_cache()
 
     torch.manual_seed(0)
@@ -500,15 +634,18 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks):
                "h2d_bytes_per_step": 2 * 4 * n * D, "d2h_bytes_per_step": 2 * 4 * n * D + 4 * D * D * world,
                "api": "gnnb200.partition.dist_gcn_conv on pinned host slices (all ranks; bytes are whole-job)"}
 
+    cpu = None
+    if rank == 0 and cpu_leg is not None:
+        cpu = cpu_leg()                                      # the oracle port on the bounded sample, host cores of rank 0
     if rank == 0:
         worst = int(torch.argmax(allst[:, 0]))
         line = {
-            "metric": "edges/sec fwd+bwd GCNConv 128-dim (RMAT)", "value": E / (ms * 1e-3), "unit": "edges/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "metric": "edges/sec fwd+bwd GCNConv 128-dim on 100M-edge graph" if D == 128 else f"edges/sec fwd+bwd GCNConv {D}-dim (RMAT N={n} E={E})",
+            "value": E / (ms * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"GCNConv {D}->{D} (add_self_loops, relu, bias) fwd+bwd on RMAT N={n} E={E} seed {seed} "
-                                   f"(BASELINE configs[1]), node-partitioned over {world} GPUs, NCCL halo exchange",
-                       "parallelism": f"node-partition x{world}, cost-balanced contiguous ranges",
+                                   f"(BASELINE configs[{1 if D == 128 else 4}]), node-partitioned over {world} GPUs, halo exchange over NVLink",
+                       "parallelism": f"node-partition x{world}, {ownership} ownership, shards built on the device from generated chunks",
                        "halo_exchange": os.environ.get("GNNB_HALO", "push") + (" (one kernel writes rows into peer halo buffers over NVLink, CUDA IPC)" if os.environ.get("GNNB_HALO", "push") == "push" else " (pack kernel + NCCL all_to_all_single)"),
                        "l2": "per-GPU features and halo buffers are far larger than the 126 MB L2",
                        "plan_build_ms": t_plan * 1e3, "chunk_edges": 128,
@@ -524,7 +661,7 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks):
                                   "ms": float(allst[:, 1].max()),
                                   "GBps_per_gpu": float(allst[:, 4].max()) * D * 4 / (float(allst[:, 1].max()) * 1e-3) / 1e9,
                                   "nvlink_peak_GBps": 770.0}},
-            "cpu_baseline": None,
+            "cpu_baseline": cpu, "parity_rel_err": None,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

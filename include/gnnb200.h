@@ -228,6 +228,41 @@ int gnnb_propagate_halo(gnnb_graph_t g, int msg, int aggr, const float* x_local,
                         int64_t n_local, const float* w, const float* cs, const float* ct, int64_t D,
                         float* out, void* stream);
 
+/* Building one rank's shards on its GPU from chunks of the global edge list (csrc/shard.cu).
+ *   ownership mode 0: contiguous ranges, bounds_host[q] <= v < bounds_host[q+1] (world + 1 entries; NULL = equal ranges);
+ *   mode 1: cyclic — node v (0-based) belongs to rank v % world as its local row v / world, which spreads the hubs of a
+ *   skewed id space over all ranks.  relabel_dev (mode 1, optional, DEVICE int32[num_nodes], alive until destroy):
+ *   a permutation node -> position; the cyclic rule is applied to the position.  With positions = rank of the node by
+ *   decreasing degree, the nodes are dealt to the ranks like cards: edge counts, node counts and the rows every rank must
+ *   serve to its peers are all balanced, whatever the id space looks like (RMAT probabilities are products over id
+ *   bits, so neither id ranges nor id % world balance it).
+ * add(): a chunk of the global COO (DEVICE arrays, index_bytes 4|8, index_base 0|1; GNNB_EINDEX if out of range); keeps,
+ *   stably, the edges whose target this rank owns (forward shard, direction 0) and those whose source it owns (backward
+ *   shard, direction 1).  Synchronises the stream.
+ * finish(direction): deduplicated sorted halo list, gathered nodes renamed into [local | halo], optional self loops
+ *   (i, i) appended after the originals, plan created (*plan_out: an ordinary gnnb_graph_t, num_dst = n_local,
+ *   num_src = n_local + n_halo; the caller destroys it).  recv_counts_host[q] (world entries) = halo rows owned by rank q.
+ * halo(direction): the owner-local row index (int32, 0-based) of every halo entry, grouped by owner in rank order — what
+ *   this rank asks each owner to send (n_halo entries, DEVICE). */
+typedef struct gnnb_shard_builder* gnnb_shard_builder_t;
+int gnnb_shard_builder_create(gnnb_shard_builder_t* out, int64_t num_nodes, int world, int rank, int mode,
+                              const int64_t* bounds_host, const int32_t* relabel_dev);
+int gnnb_shard_builder_add(gnnb_shard_builder_t b, const void* src, const void* dst, int64_t n, int index_bytes,
+                           int index_base, void* stream);
+int gnnb_shard_builder_finish(gnnb_shard_builder_t b, int direction, int add_self_loops, gnnb_graph_t* plan_out,
+                              int64_t* n_local_out, int64_t* n_halo_out, int64_t* num_edges_out, int64_t* recv_counts_host,
+                              void* stream);
+int gnnb_shard_builder_halo(gnnb_shard_builder_t b, int direction, int32_t* halo_local_dev, void* stream);
+int gnnb_shard_builder_destroy(gnnb_shard_builder_t b);
+/* The relabel table of the degree-balanced deal: cost_dev (int32[num_nodes], zeroed by the caller) accumulates in + out
+ * degree over chunks of the edge list; gnnb_balanced_relabel sorts the nodes by decreasing cost (stable) and deals them to
+ * the ranks in turn, reversing direction every round: relabel_dev[node] = position (what gnnb_shard_builder_create takes),
+ * order_dev[position] = node (rank q's local row k is node order_dev[k * world + q]). */
+int gnnb_degree_accumulate(const void* src, const void* dst, int64_t n, int index_bytes, int index_base, int64_t num_nodes,
+                           int32_t* cost_dev, void* stream);
+int gnnb_balanced_relabel(const int32_t* cost_dev, int64_t num_nodes, int world, int32_t* relabel_dev, int32_t* order_dev,
+                          void* stream);
+
 /* Halo exchange without a staging copy: every rank writes the rows a peer asked for straight into that peer's halo
  * buffer over NVLink (peer-mapped memory).  gnnb_dev_alloc / gnnb_ipc_* manage exportable device buffers (plain
  * cudaMalloc + CUDA IPC handles, 64 bytes each, exchanged by the host side); gnnb_halo_push launches ONE kernel:
@@ -298,6 +333,18 @@ int gnnb_propagate_host(gnnb_graph_t g, int transposed, int msg, int aggr, const
 int gnnb_gcn_propagate_host(gnnb_graph_t g, int transposed, const float* x_host,
                             const float* w_host, int64_t D, float* out_host);
 
+/* One GCNConv forward (+ backward when dy_host != NULL) on HOST arrays — the call a CPU-array user of the layer makes
+ * (bench.py `e2e`): replaces  y = l.σ.(l.weight * (c .* propagate(copy_xj, g', +, xj = x .* c')) .+ l.bias)  and Zygote's
+ * pullback (GNNlib/src/layers/conv.jl:14-72 on the `Dout >= Din` branch, default norm_fn, no edge weights).
+ * `g` already carries the self loops if the layer adds them.  x_host (Din,N), W_host (Dout,Din) row-major, b_host NULL or
+ * Dout, relu 0|1, dy_host (Dout,N) or NULL; outputs y_host (Dout,N), dx_host (Din,N), dW_host (Dout,Din), db_host (Dout or
+ * NULL).  Uploads, kernels and downloads run on three streams (x and dy up while y comes down); the device staging lives
+ * with the plan.  Pinned host memory makes the copies asynchronous; pageable memory works (staged by the driver).
+ * GNNB_EUNSUPPORTED for Dout < Din (use the device entries). */
+int gnnb_gcn_conv_step_host(gnnb_graph_t g, const float* x_host, const float* W_host, const float* b_host, int relu,
+                            int64_t Din, int64_t Dout, const float* dy_host, float* y_host, float* dx_host,
+                            float* dW_host, float* db_host);
+
 /* ------------------------------------------------------------- generators
  * RMAT edge list (ours; the reference has none): Graph500 a,b,c,d = .57,.19,.19,.05,
  * counter-based splitmix64 keyed on (seed, edge id, retry); edges with an endpoint >= N are redrawn;
@@ -305,6 +352,10 @@ int gnnb_gcn_propagate_host(gnnb_graph_t g, int transposed, const float* x_host,
  * The oracle has the bit-identical CPU generator (oracle/gnn_oracle.c: orc_rmat). */
 int gnnb_rmat_edges(int64_t num_nodes, int64_t num_edges, uint64_t seed, int64_t* src_dev,
                     int64_t* dst_dev, void* stream);
+/* edges [first_edge, first_edge + count) of the same list (the generator is counter-based): a 1 B-edge graph is produced
+ * and consumed chunk by chunk (gnnb_shard_builder_add) without ever being resident. */
+int gnnb_rmat_edges_range(int64_t num_nodes, int64_t first_edge, int64_t count, uint64_t seed, int64_t* src_dev,
+                          int64_t* dst_dev, void* stream);
 
 /* tuning knob for experiments: edges per work chunk of the segmented-reduce kernels (default 128;
  * power of two in [32, 4096]); affects plans created afterwards. */

@@ -814,3 +814,97 @@ def test_full_size_properties(gnn):
                                       pty.data_ptr(), None))
     a = float((px.double() * y.double()).sum()); b = float((x.double() * pty.double()).sum())
     assert abs(a - b) <= 1e-6 * max(abs(a), abs(b), 1.0)
+
+
+# ---------------------------------------------------------------------------------- oracle parity at scale
+def test_at_scale_propagate_against_the_oracle(gnn, oracle):
+    """RMAT N = 1 M, E = 10 M, D = 128 (real hubs of 10^4-10^5 edges, thousands of long rows through the fix-up kernel, every
+    kind of work item): `+` against the oracle's fused CPU path (CSC rebuild + dense x CSC, fp64), mean / max against the
+    unfused gather -> scatter path on the first 4 M edges; CSR integers with ==."""
+    n, E, D = 1_000_000, 10_000_000, 128
+    g = gnn.rmat_graph(n, E, 17)
+    s, t = oracle.rmat(n, E, 17)
+    assert np.array_equal(g.s.cpu().numpy(), s) and np.array_equal(g.t.cpu().numpy(), t)       # generator: GPU == CPU
+    rowptr = np.empty(n + 1, np.int32)
+    gnn._lib.check(gnn._lib.lib.gnnb_graph_csr(g.plan().h, 0, rowptr.ctypes.data, None, None, None))
+    assert np.array_equal(np.diff(rowptr), np.bincount(t - 1, minlength=n))                      # in-degrees, exact
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    out = gnn.propagate(gnn.copy_xj, g, operator.add, xj=jl(x))
+    assert rel(np_rows(out), oracle.propagate_fused(s, t, n, x.astype(np.float64))) < TOL
+    del out
+    Em = 4_000_000
+    gm = gnn.GNNGraph(s[:Em], t[:Em], num_nodes=n).cuda()
+    for aggr in ("mean", "max"):
+        out = gnn.propagate(gnn.copy_xj, gm, aggr, xj=jl(x))
+        assert rel(np_rows(out), oracle.propagate_unfused(aggr, s[:Em], t[:Em], n, x.astype(np.float64))) < TOL, aggr
+
+
+def test_at_scale_gcn_layer_against_the_oracle(gnn, oracle):
+    """GCNConv 128 -> 128 forward + backward on RMAT N = 1 M, E = 10 M against the oracle composition in fp64 (bar 1e-5)."""
+    n, E, D = 1_000_000, 10_000_000, 128
+    s, t = oracle.rmat(n, E, 17)
+    g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    dy = rng.standard_normal((n, D)).astype(np.float32)
+    layer = gnn.GCNConv(D, D, torch.relu, device="cuda")
+    with torch.no_grad():
+        layer.bias.normal_()
+    W, b = layer.weight.detach().cpu().numpy().astype(np.float64), layer.bias.detach().cpu().numpy().astype(np.float64)
+    xt = jl(x).requires_grad_(True)
+    y = layer(g, xt)
+    y.backward(jl(dy))
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    p, c = oracle.gcn_propagate(s2, t2, n, x.astype(np.float64))
+    pre = p @ W.T + b
+    assert rel(np_rows(y), np.maximum(pre, 0)) < 1e-5
+    dpre = dy.astype(np.float64) * (pre > 0)
+    assert rel(layer.weight.grad.cpu().numpy(), dpre.T @ p) < 1e-5
+    assert rel(layer.bias.grad.cpu().numpy(), dpre.sum(0)) < 1e-5
+    dp = (dpre @ W) * c[:, None]
+    dx = oracle.propagate_fused(t2, s2, n, dp) * c[:, None]                  # A' through the transposed edge list
+    assert rel(np_rows(xt.grad), dx) < 1e-5
+
+
+def test_at_scale_gat_layer_against_the_oracle(gnn, oracle):
+    """GATConv 8 heads x 64 on RMAT N = 100 k, E = 1 M (config-3 shape): forward against the oracle's step-by-step
+    restatement of gat_conv / gat_message in fp64."""
+    n, E, H, Cc = 100_000, 1_000_000, 8, 64
+    D = H * Cc
+    s, t = oracle.rmat(n, E, 17)
+    g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    layer = gnn.GATConv(D, Cc, torch.relu, heads=H, device="cuda")
+    with torch.no_grad():
+        y = layer(g, jl(x))
+    Wd = layer.dense_x.weight.detach().cpu().numpy().astype(np.float64)
+    a = layer.a.detach().cpu().numpy().astype(np.float64)
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    Wx = (x.astype(np.float64) @ Wd.T).reshape(n, H, Cc)
+    o, _ = oracle.gat_aggregate(s2, t2, n, Wx, np.ascontiguousarray(a.T))
+    ref = np.maximum(o.reshape(n, D) + layer.bias.detach().cpu().numpy(), 0)
+    assert rel(np_rows(y), ref) < 1e-5
+
+
+def test_at_scale_sage_on_batched_graphs_against_the_oracle(gnn, oracle):
+    """SAGEConv mean on a config-4-shaped batch (1024 graphs x 1000 nodes, 5000 edges): mean aggregation and the layer
+    output against the oracle (unfused gather -> scatter(mean), vcat, GEMM) in fp64."""
+    G, n1, e1, D = 1024, 1000, 5000, 128
+    n = G * n1
+    rng = np.random.default_rng(3)
+    off = np.repeat(np.arange(G) * n1, e1)
+    s = rng.integers(0, n1, G * e1) + off + 1
+    t = rng.integers(0, n1, G * e1) + off + 1
+    g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    m_ref = oracle.propagate_unfused("mean", s, t, n, x.astype(np.float64))
+    m = gnn.propagate(gnn.copy_xj, g, gnn.mean, xj=jl(x))
+    assert rel(np_rows(m), m_ref) < TOL
+    layer = gnn.SAGEConv(D, D, torch.relu, device="cuda")
+    with torch.no_grad():
+        y = layer(g, jl(x))
+    W, b = layer.weight.detach().cpu().numpy().astype(np.float64), layer.bias.detach().cpu().numpy().astype(np.float64)
+    ref = np.maximum(np.concatenate([x.astype(np.float64), m_ref], axis=1) @ W.T + b, 0)
+    assert rel(np_rows(y), ref) < 1e-5

@@ -120,7 +120,7 @@ def test_reference_arm_prints_the_contract_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-           "--cpu-nodes", "20000", "--cpu-edges", "100000"]
+           "--cpu-nodes", "20000", "--cpu-edges", "100000", "--ref-sample"]
     out = subprocess.check_output(cmd, text=True, timeout=300)
     line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
     assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0

@@ -25,7 +25,7 @@ def _emulate(shard, x_local, halo_rows, cs, ct):
     return out * ct[:, None]
 
 
-def _worker(rank, world, port, n, E, seed, q):
+def _worker(rank, world, port, n, E, seed, q, ownership="contiguous"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import sys
@@ -48,11 +48,14 @@ def _worker(rank, world, port, n, E, seed, q):
         return d
 
     P.build_shard = spy
-    dg = P.DistGraph(torch.as_tensor(s), torch.as_tensor(t), n, add_self_loops=True, device="cpu")
+    dg = P.DistGraph(torch.as_tensor(s), torch.as_tensor(t), n, add_self_loops=True, device="cpu", ownership=ownership)
     dg.fwd._d, dg.bwd._d = kept[0], kept[1]
     b = dg.bounds
     assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
     lo, hi = dg.lo, dg.hi
+    ids = dg.local_nodes()                                   # node of every local row
+    node_of = torch.argsort(P.to_pid(torch.arange(n), world, dg.first, ownership, dg._relabel))   # partition id -> node
+    assert torch.equal(node_of[lo:hi], ids)
     # dedup: each remote row requested once; grouped by owner in rank order
     for sh in (dg.fwd, dg.bwd):
         halo = sh._d["halo"]
@@ -63,21 +66,21 @@ def _worker(rank, world, port, n, E, seed, q):
     s0, t0 = torch.as_tensor(s) - 1, torch.as_tensor(t) - 1
     deg = torch.bincount(t0, minlength=n).double() + 1
     c_full = 1 / deg.sqrt()
-    c = c_full[lo:hi]
+    c = c_full[ids]
     cf = torch.cat([c, dg.halo(dg.fwd, c.reshape(-1, 1)).reshape(-1)])
     cb = torch.cat([c, dg.halo(dg.bwd, c.reshape(-1, 1)).reshape(-1)])
-    assert torch.equal(cf[dg.n_local:], c_full[dg.fwd._d["halo"]])
-    xl = x[lo:hi].contiguous()
+    assert torch.equal(cf[dg.n_local:], c_full[node_of[dg.fwd._d["halo"]]])
+    xl = x[ids].contiguous()
     out_f = _emulate(dg.fwd, xl, dg.halo(dg.fwd, xl), cf, c)
     out_b = _emulate(dg.bwd, xl, dg.halo(dg.bwd, xl), cb, c)
     # full-graph reference: A_hat = C (A + I) C
     A = torch.zeros(n, n, dtype=torch.float64)
     A.index_put_((s0, t0), torch.ones(E, dtype=torch.float64), accumulate=True)
     A += torch.eye(n, dtype=torch.float64)
-    ref_f = (c_full[:, None] * (A.t() @ (c_full[:, None] * x)))[lo:hi]
-    ref_b = (c_full[:, None] * (A @ (c_full[:, None] * x)))[lo:hi]
+    ref_f = (c_full[:, None] * (A.t() @ (c_full[:, None] * x)))[ids]
+    ref_b = (c_full[:, None] * (A @ (c_full[:, None] * x)))[ids]
     ok = bool(torch.allclose(out_f, ref_f, rtol=1e-12, atol=1e-12) and torch.allclose(out_b, ref_b, rtol=1e-12, atol=1e-12))
-    costs = torch.tensor([float((torch.bincount(t0, minlength=n) + torch.bincount(s0, minlength=n) + P.NODE_COST)[lo:hi].sum())])
+    costs = torch.tensor([float((torch.bincount(t0, minlength=n) + torch.bincount(s0, minlength=n) + P.NODE_COST)[ids].sum())])
     allc = [torch.zeros(1) for _ in range(world)]
     dist.all_gather(allc, costs)
     q.put((rank, ok, [float(v) for v in allc], dg.fwd.num_edges))
@@ -85,13 +88,14 @@ def _worker(rank, world, port, n, E, seed, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_partition_halo_logic_gloo(world):
+@pytest.mark.parametrize("world,ownership", [(2, "contiguous"), (3, "contiguous"), (2, "cyclic"), (3, "cyclic"),
+                                             (2, "balanced"), (3, "balanced")])
+def test_partition_halo_logic_gloo(world, ownership):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    n, E = 60, 500
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, E, 3, q)) for r in range(world)]
+    n, E = 61, 500
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, E, 3, q, ownership)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
@@ -100,7 +104,8 @@ def test_partition_halo_logic_gloo(world):
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res)
     costs = res[0][2]
-    assert max(costs) < 1.6 * (sum(costs) / world)            # cost-balanced ranges
+    if ownership != "cyclic":
+        assert max(costs) < (1.6 if ownership == "contiguous" else 1.25) * (sum(costs) / world)   # balanced cost per rank
     assert sum(e for _, _, _, e in res) == E + n               # every edge (and self loop) is owned exactly once
 
 
@@ -116,11 +121,11 @@ def test_balanced_bounds_edge_cases():
     assert b[0] == 0 and b[-1] == 3 and all(b[i] <= b[i + 1] for i in range(8))
 
 
-def _worker_layer(rank, world, port, n, E, seed, q, overlap="0", slices="1"):
+def _worker_layer(rank, world, port, n, E, seed, q, slices="1"):
     """dist_gcn_conv forward + backward under gloo, the library replaced by the CPU test double (tests/fake_abi.py):
     the whole host path of the multi-GPU layer — shard plans, c = 1/sqrt(d) with its halo copies, the two halo
     exchanges, the autograd function, the gradient all-reduce — against the dense full-graph formula."""
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GNNB_HALO="nccl", GNNB_OVERLAP=overlap, GNNB_HALO_SLICES=slices)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GNNB_HALO="nccl", GNNB_HALO_SLICES=slices)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -141,9 +146,8 @@ def _worker_layer(rank, world, port, n, E, seed, q, overlap="0", slices="1"):
         P.build_shard = lambda *a, **k: (kept.append(orig(*a, **k)) or kept[-1])
         dg = P.DistGraph(torch.as_tensor(s), torch.as_tensor(t), n, add_self_loops=True, device="cpu")
         P.build_shard = orig
-        for sh, d in ((dg.fwd, kept[0]), (dg.bwd, kept[1])):       # what DistGraph._make does on a CUDA device
-            sh.plan, sh.split = dg._plans(d)
-        assert (dg.fwd.split is not None) == (overlap == "1")
+        for sh, d in ((dg.fwd, kept[0]), (dg.bwd, kept[1])):       # the plans csrc/shard.cu creates on a CUDA device
+            sh.plan = dg._plans(d)
         torch.manual_seed(0)
         layer = gnn.GCNConv(Din, Dout, torch.relu)
         with torch.no_grad():
@@ -168,7 +172,7 @@ def _worker_layer(rank, world, port, n, E, seed, q, overlap="0", slices="1"):
         close = lambda a, r: bool(torch.allclose(a.double(), r, rtol=2e-5, atol=2e-6))
         checks = {"y": close(gnn.rows(y), yr[lo:hi]), "dx": close(gnn.rows(x.grad), xr.grad[lo:hi]),
                   "dW": close(layer.weight.grad, W.grad), "db": close(layer.bias.grad, b.grad),
-                  "calls": (fake.calls.count("gnnb_propagate_halo") == (0 if overlap == "1" else 2 * int(slices))
+                  "calls": (fake.calls.count("gnnb_propagate_halo") == 2 * int(slices)
                             and fake.calls.count("gnnb_gcn_norm") == 1)}
         ok = all(checks.values())
         err = str(checks)
@@ -177,15 +181,13 @@ def _worker_layer(rank, world, port, n, E, seed, q, overlap="0", slices="1"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,overlap,slices", [(2, "0", "1"), (3, "0", "1"), (2, "1", "1"), (3, "1", "1"),
-                                                  (2, "0", "2"), (2, "1", "2")])
-def test_dist_gcn_conv_gloo_on_the_test_double(world, overlap, slices):
-    """overlap = "1": the opt-in schedule that splits every shard into local-source and halo-source edges;
-    slices = "2": the opt-in column-sliced exchange (GNNB_HALO_SLICES)"""
+@pytest.mark.parametrize("world,slices", [(2, "1"), (3, "1"), (2, "2")])
+def test_dist_gcn_conv_gloo_on_the_test_double(world, slices):
+    """slices = "2": the column-sliced exchange (GNNB_HALO_SLICES)"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker_layer, args=(r, world, port, 50, 400, 5, q, overlap, slices))
+    procs = [ctx.Process(target=_worker_layer, args=(r, world, port, 50, 400, 5, q, slices))
              for r in range(world)]
     for p in procs:
         p.start()
