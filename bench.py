@@ -184,8 +184,14 @@ def cpu_gcn_step_port(n, E, D, steps=1, keep=False):
         dx = dxs * c[:, None]
         times.append(time.perf_counter() - t0)
         if keep:
-            res = {"s": s, "t": t, "x": x, "W": W, "b": b, "dy": dy, "y": y, "dx": dx, "dW": dW, "db": db}
-        del xs, A, p, pre, dpre, dp, dxs
+            def pullback(mask):                                           # the same pullback on a given relu mask
+                dq = dy * mask
+                dpp = (dq @ W) * c[:, None]
+                return {"dW": dq.T @ p, "db": dq.sum(0), "dx": oracle.dense_times_csc(dpp, A, transposed=True) * c[:, None]}
+            res = {"s": s, "t": t, "x": x, "W": W, "b": b, "dy": dy, "y": y, "pre": pre, "pullback": pullback}
+        else:
+            del A, p, pre
+        del xs, dpre, dp, dxs
     return min(times), oracle, res
 
 
@@ -258,6 +264,25 @@ def time_kernel(torch, fn, reps, flush=None):
         a.record(); fn(); b.record()
     torch.cuda.synchronize()
     return sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+
+
+def capture_step(torch, step, dev):
+    """the whole step as ONE CUDA graph (removes the per-launch CPU latency of small workloads); None if capture fails"""
+    try:
+        side = torch.cuda.Stream(dev)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            step()
+        cg.replay()
+        torch.cuda.synchronize()
+        return cg, None
+    except Exception as e:
+        torch.cuda.synchronize()
+        return None, f"CUDA graph capture failed: {type(e).__name__}: {str(e)[:160]}"
 
 
 def make_flush(torch, dev):
@@ -383,10 +408,13 @@ def run_config2(args, torch, gnn, dev):
             ys = ls(gs, xs)
             ys.backward(gnn.unrows(torch.as_tensor(r["dy"]).to(dev)))
             torch.cuda.synchronize()
-            return {"y": relerr(gnn.rows(ys.detach()).cpu().numpy(), r["y"]), "dx": relerr(gnn.rows(xs.grad).cpu().numpy(), r["dx"]),
-                    "dW": relerr(ls.weight.grad.cpu().numpy(), r["dW"]), "db": relerr(ls.bias.grad.cpu().numpy(), r["db"]),
+            yg = gnn.rows(ys.detach()).cpu().numpy()
+            ref = r["pullback"](yg > 0)                    # relu' is discontinuous at 0: the pullback is compared on the mask
+            return {"y": relerr(yg, r["y"]), "dx": relerr(gnn.rows(xs.grad).cpu().numpy(), ref["dx"]),       # of its forward
+                    "dW": relerr(ls.weight.grad.cpu().numpy(), ref["dW"]), "db": relerr(ls.bias.grad.cpu().numpy(), ref["db"]),
+                    "relu_mask_disagreements": int(((yg > 0) != (r["pre"] > 0)).sum()), "elements": int(yg.size),
                     "against": f"oracle port (fp32, the reference's operation order) on RMAT N={ns} E={len(r['s'])}; "
-                               "normwise relative error, bar 1e-5"}
+                               "normwise relative error, bar 1e-5; backward on the GPU forward's relu mask"}
         cpu, parity = cpu_leg_gcn(args, gpu_replay)
 
     workload = (f"GCNConv {D}->{D} (add_self_loops, relu, bias) fwd+bwd on RMAT N={n} E={E} seed {SEED} (BASELINE configs[1]); "
@@ -435,22 +463,10 @@ def run_config1(args, torch, gnn, dev):
     ms_eager, clocks = timed_region(torch, step, args.steps, dev, dev.index or 0, flush)
     launches = gnn.launch_count() - l0
     # the whole step as ONE CUDA graph launch (launch-latency bound otherwise: ~40 kernels of a few microseconds)
-    graph_ms, graph_note = None, None
-    try:
-        side = torch.cuda.Stream(dev)
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                step()
-        torch.cuda.synchronize()
-        cg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cg):
-            step()
-        cg.replay()
-        torch.cuda.synchronize()
+    graph_ms = None
+    cg, graph_note = capture_step(torch, step, dev)
+    if cg is not None:
         graph_ms, _ = timed_region(torch, cg.replay, args.steps, dev, dev.index or 0, flush)
-    except Exception as e:                                   # capture not possible on this build: eager number stands
-        graph_note = f"CUDA graph capture failed: {type(e).__name__}: {str(e)[:120]}"
-        torch.cuda.synchronize()
     ms = graph_ms if graph_ms is not None else ms_eager
     peak, peak_src = measured_peaks()
     bytes_step = 4 * (2 * n * 1433 + 4 * n * 16 + 4 * n * 7 + 3 * 1433 * 16) + 2 * 2 * (E + n) * (4 * 16 + 12)
@@ -659,8 +675,13 @@ def run_config4(args, torch, gnn, dev):
     torch.cuda.synchronize()
     flush = make_flush(torch, dev)
     l0 = gnn.launch_count()
-    ms, clocks = timed_region(torch, step, args.steps, dev, dev.index or 0, flush)
+    ms_eager, clocks = timed_region(torch, step, args.steps, dev, dev.index or 0, flush)
     launches = gnn.launch_count() - l0
+    cg, graph_note = capture_step(torch, step, dev)      # ~45 launches of 0.02-0.3 ms: CPU launch latency otherwise dominates
+    graph_ms = None
+    if cg is not None:
+        graph_ms, _ = timed_region(torch, cg.replay, args.steps, dev, dev.index or 0, flush)
+    ms = graph_ms if graph_ms is not None else ms_eager
     xr = gnn.rows(x.detach()); out = torch.empty_like(xr); p = g.plan()
     gnn._lib.check(lib.gnnb_graph_csr(p.h, 1, None, None, None, None))
     kms = time_kernel(torch, lambda: gnn._lib.check(lib.gnnb_propagate(p.h, 0, 0, gnn._lib.MEAN, xr.data_ptr(), None, None, None, D,
@@ -672,6 +693,8 @@ def run_config4(args, torch, gnn, dev):
             "kernel": "gnnb::seg_lean_kernel<1,0,false,0,MEAN> (fused mean propagate, D=128) after an L2 flush",
             "kernel_ms": kms, "algorithmic_bytes_per_launch": alg, "compulsory_bytes_per_launch": 2 * 4 * D * n + 4 * E + 4 * (n + 1),
             "share_of_step": 2 * kms / ms,
+            "launch_bound": {"eager_ms": ms_eager, "cuda_graph_ms": graph_ms, "launches_per_step": launches / args.steps,
+                             "note": graph_note or "one cudaGraphLaunch per step"},
             "note": "components of 1000 nodes (512 KB of features) fit L2: the gather-model fraction can exceed 1"}
     e2e = None
     if not args.no_e2e:
@@ -710,27 +733,34 @@ def run_config4(args, torch, gnn, dev):
         cat = np.concatenate([xs, m], axis=1)                             # vcat(xi, m), conv.jl:281
         pre = cat @ W.T + b
         ys = np.maximum(pre, 0)
-        dpre = dys * (pre > 0)
-        dW = dpre.T @ cat
-        dcat = dpre @ W
         deg = np.maximum(np.bincount(tn - 1, minlength=ns), 1).astype(np.float32)
-        dxs = dcat[:, :D] + oracle.propagate_unfused("+", tn, sn, ns, dcat[:, D:] / deg[:, None])
+
+        def pullback(mask):
+            dq = dys * mask
+            dc = dq @ W
+            return dq.T @ cat, dc[:, :D] + oracle.propagate_unfused("+", tn, sn, ns, dc[:, D:] / deg[:, None])
+        dW, dxs = pullback(pre > 0)
         dt = time.perf_counter() - t0
         gs = gnn.GNNGraph(ss.to(dev), ts.to(dev), num_nodes=ns)
         xg = gnn.unrows(torch.as_tensor(xs).to(dev)).requires_grad_(True)
         layer.weight.grad = None
         yg = layer(gs, xg)
         yg.backward(gnn.unrows(torch.as_tensor(dys).to(dev)))
-        parity = {"y": relerr(gnn.rows(yg.detach()).cpu().numpy(), ys), "dx": relerr(gnn.rows(xg.grad).cpu().numpy(), dxs),
+        ygn = gnn.rows(yg.detach()).cpu().numpy()
+        dW, dxs = pullback(ygn > 0)                        # relu' is discontinuous at 0: same mask as the GPU forward
+        parity = {"y": relerr(ygn, ys), "dx": relerr(gnn.rows(xg.grad).cpu().numpy(), dxs),
                   "dW": relerr(layer.weight.grad.cpu().numpy(), dW),
-                  "against": f"oracle port on {Gs} batched graphs (N={ns} E={Es}), fwd+bwd; bar 1e-5"}
+                  "relu_mask_disagreements": int(((ygn > 0) != (pre > 0)).sum()), "elements": int(ygn.size),
+                  "against": f"oracle port on {Gs} batched graphs (N={ns} E={Es}), fwd+bwd; bar 1e-5; backward on the GPU "
+                             "forward's relu mask"}
         cpu = {"value": Es / dt, "unit": "edges/s", "cores": blas_threads(), "kind": "port", "seconds": dt,
                "sample": f"{Gs} of the 1024 graphs: unfused gather + serial scatter(mean) as the reference, vcat, BLAS GEMMs; scaled by edges"}
     workload = (f"SAGEConv {D}->{D} mean (relu, bias) fwd+bwd on {G} batched ER graphs ({n1} nodes, {e1} edges each): N={n} E={E} "
                 "(BASELINE configs[3]; D is this project's choice)")
     return base_line(args, E / (ms * 1e-3), ms, 1, workload,
                      {"l2": "256 MB written between timed iterations (outside the event pairs): the 524 MB of features are "
-                            "only 4x the L2"}, clocks, e2e, launches, roof, cpu, parity)
+                            "only 4x the L2", "timed": "CUDA graph replay of the step" if graph_ms is not None else "eager"},
+                     clocks, e2e, launches, roof, cpu, parity)
 
 
 # ============================================================================================================= reference arm

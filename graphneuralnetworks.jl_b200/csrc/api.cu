@@ -95,7 +95,7 @@ int gnnb_device_count(void) {
 }
 int64_t gnnb_launch_count(void) { return g_launches.load(); }
 int gnnb_set_kernel_variant(int v) {
-    if (v != 0 && v != 1 && v != 5 && v != 10 && v != 12) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be one of 0, 1, 5, 10, 12");
+    if (v != 0 && v != 1 && v != 5 && v != 10 && v != 12 && v != 13) GNNB_FAIL(GNNB_EINVAL, "kernel variant must be one of 0, 1, 5, 10, 12, 13");
     gnnb::g_variant = v;
     return GNNB_OK;
 }

@@ -22,7 +22,7 @@ namespace gnnb {
 namespace tc {
 constexpr int BM = 128;           // rows per tile (UMMA M)
 constexpr int BK = 32;            // floats per K-block = one 128 B swizzle row
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 2;            // (3 until the epilogue staging below needed the room; the loaders prefetch one more block in registers)
 constexpr int LOADERS = 256;      // warps 0-7
 constexpr int MMA_WARP = 8;
 constexpr int EPI_WARP0 = 9;      // warps 9-12
@@ -32,7 +32,9 @@ constexpr int W_BYTES = 4 * KBLK_BYTES;       // up to K = 128: 64 KB per image
 constexpr int SMEM_W_BIG = 0;
 constexpr int SMEM_W_SMALL = W_BYTES;
 constexpr int SMEM_A = 2 * W_BYTES;           // stages: [big 16 KB][small 16 KB]
-constexpr int SMEM_BIAS = SMEM_A + NSTAGE * 2 * KBLK_BYTES;
+constexpr int EPI_LD = 36;            // floats per staged row: 32 + 4 of padding keeps float4 accesses conflict-free
+constexpr int SMEM_EPI = SMEM_A + NSTAGE * 2 * KBLK_BYTES;   // 4 epilogue warps x 32 rows x EPI_LD floats
+constexpr int SMEM_BIAS = SMEM_EPI + 4 * 32 * EPI_LD * 4;
 constexpr int SMEM_BAR = SMEM_BIAS + 512;
 constexpr int SMEM_TOTAL = SMEM_BAR + 128;
 
@@ -213,26 +215,35 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
             const int acc = tcount & 1;
             if (!bar_wait(bar_tfull + 8 * acc, (tcount >> 1) & 1, p.err)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int64_t row = tile * BM + q * 32 + lane;
-            float* yrow = p.y + (size_t)row * p.Nout;
+            // A thread holds 32 consecutive columns of ONE row after tcgen05.ld; stored from there, a warp's STG.128 touches
+            // 32 different rows (ncu, round 1: 108 M store wavefronts, L1TEX 80 % busy — the kernel's limiter).  The chunk
+            // is therefore transposed through a padded shared-memory tile and written as whole 128 B row segments.
+            float* stg = reinterpret_cast<float*>(smem + SMEM_EPI) + q * (32 * EPI_LD);
+            const int64_t row0 = tile * BM + q * 32;
             for (int c0 = 0; c0 < p.Nout; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + c0, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < p.M) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (c0 + j < p.Nout) {
-                            float4 o;
-                            o.x = __uint_as_float(r[j]) + sbias[c0 + j];
-                            o.y = __uint_as_float(r[j + 1]) + sbias[c0 + j + 1];
-                            o.z = __uint_as_float(r[j + 2]) + sbias[c0 + j + 2];
-                            o.w = __uint_as_float(r[j + 3]) + sbias[c0 + j + 3];
-                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                            *reinterpret_cast<float4*>(yrow + c0 + j) = o;
-                        }
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(r[j]) + sbias[c0 + j];
+                    o.y = __uint_as_float(r[j + 1]) + sbias[c0 + j + 1];
+                    o.z = __uint_as_float(r[j + 2]) + sbias[c0 + j + 2];
+                    o.w = __uint_as_float(r[j + 3]) + sbias[c0 + j + 3];
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = o;
                 }
+                __syncwarp();
+                const int f = (lane & 7) * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = (lane >> 3) + 4 * i;
+                    const float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + f);
+                    if (row0 + rr < p.M && c0 + f < p.Nout)
+                        *reinterpret_cast<float4*>(p.y + (size_t)(row0 + rr) * p.Nout + c0 + f) = o;
+                }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(bar_tempty + 8 * acc);

@@ -22,6 +22,8 @@
 
 namespace gnnb {
 
+extern int g_variant;   // segreduce.cu: 0 = lean work-item kernels, 12 = the round-1 chunk kernels
+
 struct GatParams {
     const int32_t* __restrict__ rowptr;
     const int32_t* __restrict__ col;
@@ -44,6 +46,8 @@ struct GatParams {
     int32_t E, nrows, chunk, nchunks;
     int32_t fill;
     float slope;
+    const int4* __restrict__ items;   // lean kernels: the plan's work items {e_begin, e_end, slot, 0} (seglean.cu)
+    int32_t n_items;
 };
 
 template <int VEC> struct GV;
@@ -183,6 +187,141 @@ __global__ void __launch_bounds__(128, (K == 1 ? 8 : 1)) gat_fwd_kernel(const Ga
     if (has_work) {
         flush(r, true);
         if (b.e_end == p.E) fill_gap(r, p.nrows);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward, lean
+// The same pass on the plan's work-item list (seglean.cu): an item is a run of whole rows or one piece of a long row, so
+// the flush path has no case analysis, a warp starts with one 16 B load, row ends are one ballot per 32 edges and all
+// control flow is warp-uniform.  The logits of a batch of 32 edges are computed ONCE, lane = edge (H values each, from
+// el[target] and er[source]), parked in shared memory and read back by head — the old kernel recomputed every logit on
+// every lane of the head and re-read the index arrays for each 128-float tile of the row.  One warp covers the whole
+// row of KV*128 floats.  Partial slots keep the layout [acc: D][M: H][S: H], so gat_fwd_fixup_kernel is shared.
+template <int KV>
+__global__ void __launch_bounds__(256, 2) gat_fwd_lean_kernel(const GatParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int U = 8 / KV;
+    constexpr int64_t STRIDE = (int64_t)KV * 128;
+    extern __shared__ float su[];                      // [warp][edge of the batch][head]
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= p.n_items) return;
+    const int H = p.H;
+    float* myu = su + (threadIdx.x >> 5) * 32 * H;
+    const int4 it = __ldg(p.items + item);
+    const int e_end = it.y;
+    const bool partial = __any_sync(FULL, it.z >= 0);
+    int hd[KV]; bool lead[KV];
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+        const int f = i * 128 + lane * 4;
+        hd[i] = f / p.C;
+        lead[i] = (f % p.C) == 0;
+    }
+    const float* const xl = p.Wx + lane * 4;
+    float4 acc[KV]; float M[KV], S[KV];
+#pragma unroll
+    for (int i = 0; i < KV; ++i) { acc[i] = gzero4(); M[i] = -CUDART_INF_F; S[i] = 0.f; }
+
+    auto load_lane = [&](int e0, int& c, int& r, bool& last) {
+        const int my = e0 + lane;
+        c = 0; r = 0; last = false;
+        if (my < e_end) {
+            c = __ldg(p.col + my);
+            r = __ldg(p.row + my);
+            last = (my + 1 == e_end) || (__ldg(p.row + my + 1) != r);
+        }
+    };
+    int e = it.x;
+    int c_n, r_n; bool last_n;
+    load_lane(e, c_n, r_n, last_n);
+    bool more = true;
+    while (more) {
+        const int c_l = c_n, r_l = r_n;
+        const bool mine = e + lane < e_end;
+        const unsigned vmask = __ballot_sync(FULL, mine);
+        const unsigned bmask = partial ? 0u : __ballot_sync(FULL, last_n);
+        more = __any_sync(FULL, e + 32 < e_end);
+        if (more) load_lane(e + 32, c_n, r_n, last_n);
+        if (mine) {                                    // this edge's logits, all heads
+            const float* elr = p.el + (int64_t)r_l * H;
+            const float* erc = p.er + (int64_t)c_l * H;
+            for (int h = 0; h < H; ++h) {
+                const float z = __ldg(elr + h) + __ldg(erc + h);
+                myu[lane * H + h] = z > 0.f ? z : p.slope * z;
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32 && (vmask >> j0) != 0u; j0 += U) {
+            float4 v[U][KV];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int cj = __shfl_sync(FULL, c_l, j0 + u);
+                const float* xr = xl + (int64_t)cj * STRIDE;
+                if ((vmask >> (j0 + u)) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) v[u][i] = __ldg(reinterpret_cast<const float4*>(xr + i * 128));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if ((vmask >> (j0 + u)) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        const float uu = myu[(j0 + u) * H + hd[i]];
+                        const float Mn = fmaxf(M[i], uu);
+                        const float sc = __expf(M[i] - Mn);          // exp(-inf) = 0 on the first edge of a row
+                        const float pp = __expf(uu - Mn);
+                        S[i] = fmaf(S[i], sc, pp);
+                        acc[i] = gfma(acc[i], sc, v[u][i], pp);
+                        M[i] = Mn;
+                    }
+                }
+                if ((bmask >> (j0 + u)) & 1u) {                      // row end: normalise and store, exactly once
+                    const int rj = __shfl_sync(FULL, r_l, j0 + u);
+                    float* o = p.out + (int64_t)rj * STRIDE + lane * 4;
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        *reinterpret_cast<float4*>(o + i * 128) = gdiv(acc[i], S[i]);
+                        if (lead[i]) {
+                            p.stat_a[(int64_t)rj * H + hd[i]] = M[i];
+                            p.stat_b[(int64_t)rj * H + hd[i]] = S[i];
+                        }
+                        acc[i] = gzero4(); M[i] = -CUDART_INF_F; S[i] = 0.f;
+                    }
+                }
+            }
+        }
+        __syncwarp();                                  // the next batch overwrites the logits
+        e += 32;
+    }
+    if (partial) {
+        const int64_t slot = (p.D + 2 * (int64_t)H + 3) & ~(int64_t)3;
+        float* base = p.ws + (int64_t)it.z * slot;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+            *reinterpret_cast<float4*>(base + i * 128 + lane * 4) = acc[i];
+            if (lead[i]) { base[p.D + hd[i]] = M[i]; base[p.D + H + hd[i]] = S[i]; }
+        }
+    }
+}
+
+// rows without edges: out = 0, statistics = 0 (what the old kernel's fill_gap wrote); one warp per 32 rows
+__global__ void __launch_bounds__(256) gat_fill_empty_kernel(const int32_t* __restrict__ rowptr, int32_t nrows,
+                                                             float* __restrict__ out, int64_t D, float* __restrict__ sa,
+                                                             float* __restrict__ sb, int H) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    const int64_t r = r0 + lane;
+    const bool empty = r < nrows && __ldg(rowptr + r) == __ldg(rowptr + r + 1);
+    unsigned m = __ballot_sync(0xffffffffu, empty);
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        float* base = out + (size_t)(r0 + j) * D;
+        for (int64_t f = (int64_t)lane * 4; f < D; f += 128) *reinterpret_cast<float4*>(base + f) = gzero4();
+        for (int h = lane; h < H; h += 32) { sa[(r0 + j) * H + h] = 0.f; if (sb) sb[(r0 + j) * H + h] = 0.f; }
     }
 }
 
@@ -368,6 +507,134 @@ __global__ void __launch_bounds__(128, (K == 1 ? 5 : 1)) gat_bwd_kernel(const Ga
     }
 }
 
+// ----------------------------------------------------------------------------------------------- backward, lean
+// The same pass on the work-item list of the CSR-by-source plan.  Per batch of 32 edges the per-edge-per-head scalars are
+// computed ONCE, lane = edge: α (from el, er and the forward's M, S), α·leakyrelu'(z) and T of the target — parked in shared
+// memory; the old kernel gathered el / M / S / T and re-evaluated exp on every lane of the head, per 128-float tile.
+// The source's own Wx row is read beside every gathered dout row (an L1 hit after the row's first edge) instead of being
+// loaded at the row change, where the in-order warp sat out a full memory latency every ~11 edges.
+// Partial slots keep the layout [acc: D][der: H] of gat_bwd_fixup_kernel.  C <= 128 (a head never spans two slices).
+template <int KV>
+__global__ void __launch_bounds__(256, 2) gat_bwd_lean_kernel(const GatParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int U = (KV >= 4) ? 2 : (KV == 2 ? 2 : 4);
+    constexpr int64_t STRIDE = (int64_t)KV * 128;
+    extern __shared__ float su[];                      // [warp][3][edge of the batch][head]: α, α·lrelu', T
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= p.n_items) return;
+    const int H = p.H;
+    float* sa = su + (threadIdx.x >> 5) * 3 * 32 * H;
+    float* sb = sa + 32 * H;
+    float* st_ = sb + 32 * H;
+    const int4 it = __ldg(p.items + item);
+    const int e_end = it.y;
+    const bool partial = __any_sync(FULL, it.z >= 0);
+    const int L = p.C >> 2;                            // lanes per head (power of two <= 32)
+    int hd[KV]; bool lead[KV];
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+        const int f = i * 128 + lane * 4;
+        hd[i] = f / p.C;
+        lead[i] = (f % p.C) == 0;
+    }
+    const float* const dl = p.dout + lane * 4;
+    const float* const wl = p.Wx + lane * 4;
+    float4 acc[KV]; float dacc[KV];
+#pragma unroll
+    for (int i = 0; i < KV; ++i) { acc[i] = gzero4(); dacc[i] = 0.f; }
+
+    auto load_lane = [&](int e0, int& c, int& r, int& id, bool& last) {
+        const int my = e0 + lane;
+        c = 0; r = 0; id = 0; last = false;
+        if (my < e_end) {
+            c = __ldg(p.col + my);
+            r = __ldg(p.row + my);
+            id = __ldg(p.eid + my);
+            last = (my + 1 == e_end) || (__ldg(p.row + my + 1) != r);
+        }
+    };
+    int e = it.x;
+    int c_n, r_n, id_n; bool last_n;
+    load_lane(e, c_n, r_n, id_n, last_n);
+    bool more = true;
+    while (more) {
+        const int c_l = c_n, r_l = r_n, id_l = id_n;
+        const bool mine = e + lane < e_end;
+        const unsigned vmask = __ballot_sync(FULL, mine);
+        const unsigned bmask = partial ? 0u : __ballot_sync(FULL, last_n);
+        more = __any_sync(FULL, e + 32 < e_end);
+        if (more) load_lane(e + 32, c_n, r_n, id_n, last_n);
+        if (mine) {                                    // this edge's attention scalars, all heads
+            const int64_t ti = (int64_t)c_l * H, sj = (int64_t)r_l * H;
+            for (int h = 0; h < H; ++h) {
+                const float z = __ldg(p.el + ti + h) + __ldg(p.er + sj + h);
+                const float uu = z > 0.f ? z : p.slope * z;
+                const float al = __fdiv_rn(__expf(uu - __ldg(p.smax + ti + h)), __ldg(p.ssum + ti + h));
+                sa[lane * H + h] = al;
+                sb[lane * H + h] = al * (z > 0.f ? 1.f : p.slope);
+                st_[lane * H + h] = __ldg(p.tnode + ti + h);
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32 && (vmask >> j0) != 0u; j0 += U) {
+            float4 v[U][KV], w[U][KV];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ci = __shfl_sync(FULL, c_l, j0 + u);
+                const int rj = __shfl_sync(FULL, r_l, j0 + u);
+                const float* dr = dl + (int64_t)ci * STRIDE;
+                const float* wr = wl + (int64_t)rj * STRIDE;
+                if ((vmask >> (j0 + u)) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        v[u][i] = __ldg(reinterpret_cast<const float4*>(dr + i * 128));
+                        w[u][i] = __ldg(reinterpret_cast<const float4*>(wr + i * 128));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ek = __shfl_sync(FULL, id_l, j0 + u);
+                if ((vmask >> (j0 + u)) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        float da = gdot(v[u][i], w[u][i]);
+                        for (int o = L >> 1; o > 0; o >>= 1) da += __shfl_xor_sync(FULL, da, o);
+                        const int q = (j0 + u) * H + hd[i];
+                        const float dzv = sb[q] * (da - st_[q]);
+                        acc[i] = gfma(acc[i], 1.f, v[u][i], sa[q]);
+                        dacc[i] += dzv;
+                        if (lead[i]) p.dz[(int64_t)ek * H + hd[i]] = dzv;
+                    }
+                }
+                if ((bmask >> (j0 + u)) & 1u) {                      // row end: dWx row and der, exactly once
+                    const int rj = __shfl_sync(FULL, r_l, j0 + u);
+                    float* o = p.out + (int64_t)rj * STRIDE + lane * 4;
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        *reinterpret_cast<float4*>(o + i * 128) = acc[i];
+                        if (lead[i]) p.stat_a[(int64_t)rj * H + hd[i]] = dacc[i];
+                        acc[i] = gzero4(); dacc[i] = 0.f;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        e += 32;
+    }
+    if (partial) {
+        const int64_t slot = (p.D + (int64_t)H + 3) & ~(int64_t)3;
+        float* base = p.ws + (int64_t)it.z * slot;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+            *reinterpret_cast<float4*>(base + i * 128 + lane * 4) = acc[i];
+            if (lead[i]) base[p.D + hd[i]] = dacc[i];
+        }
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) gat_bwd_fixup_kernel(const GatParams p, const int32_t* __restrict__ long_rows,
                                                             int n_long) {
@@ -458,9 +725,30 @@ int gnnb_gat_aggregate(gnnb_graph_t g, const float* Wx, const float* el, const f
         GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + 2 * H + 4)));
         p.ws = g->ws;
     }
-    const dim3 grid((unsigned)ceil_div(p.nchunks, 4), (unsigned)ceil_div(D, (int64_t)32 * vec * kk));
-    GAT_DISPATCH(gat_fwd_kernel, vec, kk, grid, st, p);
-    GNNB_LAUNCHED();
+    const bool lean = g_variant == 0 && vec == 4 && (D == 128 || D == 256 || D == 512) && (C & (C - 1)) == 0 && H <= 64;
+    if (lean) {                                    // the work-item kernel (one warp per whole row, logits once per edge)
+        GNNB_TRY(ensure_items(g, c, st));
+        p.items = reinterpret_cast<const int4*>(c.items); p.n_items = c.n_items;
+        if (c.n_empty > 0) {
+            gat_fill_empty_kernel<<<(unsigned)ceil_div((int64_t)c.nrows, 256), 256, 0, st>>>(c.rowptr, c.nrows, out, D, seg_max, seg_sum, (int)H);
+            GNNB_LAUNCHED();
+        }
+        const unsigned blocks = (unsigned)ceil_div(c.n_items, 8);
+        const size_t smem = sizeof(float) * 8 * 32 * (size_t)H;
+        if (smem > 48 * 1024) {
+            GNNB_CUDA(cudaFuncSetAttribute(gat_fwd_lean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNNB_CUDA(cudaFuncSetAttribute(gat_fwd_lean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNNB_CUDA(cudaFuncSetAttribute(gat_fwd_lean_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (D == 128) gat_fwd_lean_kernel<1><<<blocks, 256, smem, st>>>(p);
+        else if (D == 256) gat_fwd_lean_kernel<2><<<blocks, 256, smem, st>>>(p);
+        else gat_fwd_lean_kernel<4><<<blocks, 256, smem, st>>>(p);
+        GNNB_LAUNCHED();
+    } else {
+        const dim3 grid((unsigned)ceil_div(p.nchunks, 4), (unsigned)ceil_div(D, (int64_t)32 * vec * kk));
+        GAT_DISPATCH(gat_fwd_kernel, vec, kk, grid, st, p);
+        GNNB_LAUNCHED();
+    }
     if (c.n_long > 0) {
         const unsigned fb = nblk((int64_t)c.n_long * (D / vec));
         if (vec == 4) gat_fwd_fixup_kernel<4><<<fb, 256, 0, st>>>(p, c.long_rows, c.n_long);
@@ -518,9 +806,30 @@ int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, con
         GNNB_TRY(ensure_ws(g, sizeof(float) * (size_t)2 * p.nchunks * (D + H + 4)));
         p.ws = g->ws;
     }
-    const dim3 grid((unsigned)ceil_div(p.nchunks, 4), (unsigned)ceil_div(D, (int64_t)32 * vec * kk));
-    GAT_DISPATCH(gat_bwd_kernel, vec, kk, grid, st, p);
-    GNNB_LAUNCHED();
+    const bool lean = g_variant == 0 && vec == 4 && (D == 128 || D == 256 || D == 512) && (C & (C - 1)) == 0 && C <= 128 && H <= 64;
+    if (lean) {
+        GNNB_TRY(ensure_items(g, c, st));
+        p.items = reinterpret_cast<const int4*>(c.items); p.n_items = c.n_items;
+        if (c.n_empty > 0) {
+            gat_fill_empty_kernel<<<(unsigned)ceil_div((int64_t)c.nrows, 256), 256, 0, st>>>(c.rowptr, c.nrows, dWx, D, der, nullptr, (int)H);
+            GNNB_LAUNCHED();
+        }
+        const unsigned blocks = (unsigned)ceil_div(c.n_items, 8);
+        const size_t smem = sizeof(float) * 8 * 3 * 32 * (size_t)H;
+        if (smem > 48 * 1024) {
+            GNNB_CUDA(cudaFuncSetAttribute(gat_bwd_lean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNNB_CUDA(cudaFuncSetAttribute(gat_bwd_lean_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNNB_CUDA(cudaFuncSetAttribute(gat_bwd_lean_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (D == 128) gat_bwd_lean_kernel<1><<<blocks, 256, smem, st>>>(p);
+        else if (D == 256) gat_bwd_lean_kernel<2><<<blocks, 256, smem, st>>>(p);
+        else gat_bwd_lean_kernel<4><<<blocks, 256, smem, st>>>(p);
+        GNNB_LAUNCHED();
+    } else {
+        const dim3 grid((unsigned)ceil_div(p.nchunks, 4), (unsigned)ceil_div(D, (int64_t)32 * vec * kk));
+        GAT_DISPATCH(gat_bwd_kernel, vec, kk, grid, st, p);
+        GNNB_LAUNCHED();
+    }
     if (c.n_long > 0) {
         const unsigned fb = nblk((int64_t)c.n_long * (D / vec));
         if (vec == 4) gat_bwd_fixup_kernel<4><<<fb, 256, 0, st>>>(p, c.long_rows, c.n_long);

@@ -18,10 +18,13 @@
 // Reference semantics: NNlib.gather -> message -> NNlib.scatter (GNNlib/src/msgpass.jl:75-79,121-129,145-149).
 #include "common.cuh"
 #include "segwalk.cuh"
+#include "tma.cuh"
 #include <cub/cub.cuh>
 #include <math_constants.h>
 
 namespace gnnb {
+
+extern int g_variant;   // segreduce.cu
 
 struct LeanParams {
     const int4* __restrict__ items;
@@ -250,6 +253,115 @@ __global__ void __launch_bounds__(256, 4) seg_lean_kernel(const LeanParams p) {
     }
 }
 
+// ---- A/B variant 13: the same pass with the rows staged in shared memory by TMA (D = 128, SUM) ---------------------------
+// BASELINE's north_star asks for "TMA staging of node-feature tiles into shared memory".  Round 1 measured one
+// cp.async.bulk per 512 B row: TMA-unit bound (~56 cycles per request per SM), 2.2x slower than register staging.  This
+// is the Blackwell form of the idea: cp.async.bulk.tensor.2d ... tile::gather4 moves FOUR indexed rows (2 KB) per request.
+// Persistent CTAs (one per SM, 8 warps); every warp is its own producer and consumer: lane 0 issues the gather4 of the
+// next four edges into the warp's private ring of 8 stages (16 KB, 32 rows in flight per warp, 256 per SM — no registers
+// held by loads in flight), all lanes wait on the stage's mbarrier (complete_tx) and reduce the four rows with LDS.128.
+// A stage is refilled with the NEXT batch's rows as soon as it has been consumed.  Same items, same arithmetic order:
+// bit-identical to the register-staged kernel.
+constexpr int G4_WARPS = 8, G4_STAGES = 8, G4_STAGE_BYTES = 4 * 512;
+
+template <int SMODE>
+__global__ void __launch_bounds__(G4_WARPS * 32, 1) seg_gather4_kernel(const LeanParams p, const __grid_constant__ CUtensorMap map) {
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(1024) unsigned char g4smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* ring = g4smem + warp * (G4_STAGES * G4_STAGE_BYTES);
+    const uint32_t ring_u = tma::smem_u32(ring);
+    const uint32_t bar0 = tma::smem_u32(g4smem + G4_WARPS * G4_STAGES * G4_STAGE_BYTES) + warp * G4_STAGES * 8;
+    if (lane == 0) {
+        for (int s = 0; s < G4_STAGES; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma::fence_proxy_async();
+    }
+    __syncwarp();
+    uint32_t par = 0;                                  // parity of every stage's next completion
+    const float4* rowl = reinterpret_cast<const float4*>(ring) + lane;     // this lane's 16 B of row 0 of stage 0
+
+    // four rows of group q of a batch whose gathered nodes sit in `c` (nv valid edges): issued by lane 0
+    auto issue = [&](int q, int c, int nv) {
+        const int last = nv - 1;
+        const int k = 4 * q;
+        const int c0 = __shfl_sync(FULL, c, k <= last ? k : last);
+        const int c1 = __shfl_sync(FULL, c, k + 1 <= last ? k + 1 : last);
+        const int c2 = __shfl_sync(FULL, c, k + 2 <= last ? k + 2 : last);
+        const int c3 = __shfl_sync(FULL, c, k + 3 <= last ? k + 3 : last);
+        if (lane == 0) {
+            tma::fence_proxy_async();                  // the stage was read through the generic proxy
+            tma::mbar_expect_tx(bar0 + 8 * q, G4_STAGE_BYTES);
+            tma::gather4(ring_u + q * G4_STAGE_BYTES, &map, 0, c0, c1, c2, c3, bar0 + 8 * q);
+        }
+    };
+
+    for (int item = blockIdx.x * G4_WARPS + warp; item < p.n_items; item += gridDim.x * G4_WARPS) {
+        const int4 it = __ldg(p.items + item);
+        const int e_end = it.y;
+        const bool partial = __any_sync(FULL, it.z >= 0);
+        auto load_lane = [&](int e0, int& c, int& r, float& s1, bool& last) {
+            const int my = e0 + lane;
+            c = 0; r = 0; s1 = 1.f; last = false;
+            if (my < e_end) {
+                c = __ldg(p.col + my);
+                r = __ldg(p.row + my);
+                if (SMODE == 1) s1 = __ldg(p.es + my);
+                last = (my + 1 == e_end) || (__ldg(p.row + my + 1) != r);
+                if (SMODE == 2) s1 = __ldg(p.cs + c);
+            }
+        };
+        float4 acc = f4(0.f);
+        int e = it.x;
+        int c_n, r_n; float s1_n; bool last_n;
+        load_lane(e, c_n, r_n, s1_n, last_n);
+        {
+            const int nv = (e_end - e) < 32 ? (e_end - e) : 32;
+            for (int q = 0; 4 * q < nv; ++q) issue(q, c_n, nv);
+        }
+        bool more = true;
+        while (more) {
+            const int r_l = r_n;
+            const float s1_l = s1_n;
+            const unsigned vmask = __ballot_sync(FULL, e + lane < e_end);
+            const unsigned bmask = partial ? 0u : __ballot_sync(FULL, last_n);
+            float sc_l = 1.f;
+            if (!partial && e + lane < e_end && p.ct) sc_l = __ldg(p.ct + r_l);
+            more = __any_sync(FULL, e + 32 < e_end);
+            if (more) load_lane(e + 32, c_n, r_n, s1_n, last_n);
+            const int nn = more ? ((e_end - e - 32) < 32 ? (e_end - e - 32) : 32) : 0;
+#pragma unroll 1
+            for (int q = 0; q < 8 && (vmask >> (4 * q)) != 0u; ++q) {
+                const uint32_t bar = bar0 + 8 * q;
+                const uint32_t ph = (par >> q) & 1u;
+                {   // bounded: a request that never completes aborts the kernel instead of hanging the GPU
+                    uint32_t spin = 0;
+                    while (!tma::mbar_try(bar, ph)) { if (++spin > (1u << 24)) __trap(); }
+                }
+                par ^= 1u << q;
+                const float4* src = rowl + q * (G4_STAGE_BYTES / 16);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = 4 * q + u;
+                    const float s1 = (SMODE != 0) ? __shfl_sync(FULL, s1_l, j) : 1.f;
+                    if ((vmask >> j) & 1u) acc = lcomb<SMODE, false, AG_SUM>(acc, src[u * 32], s1, 1.f, 1.f);
+                    if ((bmask >> j) & 1u) {
+                        const int rj = __shfl_sync(FULL, r_l, j);
+                        const float sc = __shfl_sync(FULL, sc_l, j);
+                        *reinterpret_cast<float4*>(p.out + (int64_t)rj * 128 + lane * 4) =
+                            make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
+                        acc = f4(0.f);
+                    }
+                }
+                __syncwarp();                          // every lane is done with the stage
+                if (4 * q < nn) issue(q, c_n, nn);     // refill it with the next batch's rows
+            }
+            e += 32;
+        }
+        if (partial) *reinterpret_cast<float4*>(p.ws + (int64_t)it.z * 128 + lane * 4) = acc;
+    }
+}
+
 template <int KV, int SMODE, bool HAS_W, int HALO, int AGG>
 int launch_lean3(const LeanParams& p, cudaStream_t st) {
     const unsigned blocks = (unsigned)ceil_div(p.n_items, 8);
@@ -370,6 +482,28 @@ int seg_reduce_lean(gnnb_graph* g, const Csr& c, const SegArgs& a, float* ws, bo
     p.sign = (a.aggr == GNNB_MIN) ? -1.f : 1.f;
     if (p.n_items == 0) return GNNB_OK;
     const int use_halo = halo ? 1 : 0;
+    if (g_variant == 13 && a.D == 128 && agg == AG_SUM && !halo && a.w == nullptr) {
+        CUtensorMap map;
+        if (tma::make_map_2d_f32(&map, a.x, (uint64_t)c.ncols, 128, 512, 128, 1) != 0)
+            GNNB_FAIL(GNNB_ECUDA, "cuTensorMapEncodeTiled failed for the gather4 variant");
+        const size_t smem = (size_t)G4_WARPS * G4_STAGES * G4_STAGE_BYTES + G4_WARPS * G4_STAGES * 8;
+        static int nsm = 0;
+        if (!nsm) {
+            int dev = 0;
+            GNNB_CUDA(cudaGetDevice(&dev));
+            GNNB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+            GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        int64_t want = ceil_div((int64_t)p.n_items, G4_WARPS);
+        const unsigned blocks = (unsigned)(want < nsm ? want : nsm);
+        if (smode == 0) seg_gather4_kernel<0><<<blocks, G4_WARPS * 32, smem, st>>>(p, map);
+        else if (smode == 1) seg_gather4_kernel<1><<<blocks, G4_WARPS * 32, smem, st>>>(p, map);
+        else seg_gather4_kernel<2><<<blocks, G4_WARPS * 32, smem, st>>>(p, map);
+        GNNB_LAUNCHED();
+        return GNNB_OK;
+    }
     int rc;
     if (a.D == 128) rc = launch_lean1<1>(p, smode, a.w != nullptr, use_halo, agg, st);
     else if (a.D == 256) rc = launch_lean1<2>(p, smode, a.w != nullptr, use_halo, agg, st);

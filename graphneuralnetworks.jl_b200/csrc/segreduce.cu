@@ -33,7 +33,8 @@ namespace gnnb {
 // kernel variant (gnnb_set_kernel_variant, A/B runs): 0 = default: the lean work-item kernel (seglean.cu) for rows of
 // 128 / 256 / 512 floats, taking the per-edge scale stream when the caller has one, and seg_reduce_kernel below for every
 // other shape; 10 = the lean kernel gathering cs[col] itself; 12 = seg_reduce_kernel everywhere (the round-1 default);
-// 5 = the same without the 64-register cap; 1 = shared-memory ring filled by cp.async.bulk (segbulk.cu).
+// 5 = the same without the 64-register cap; 1 = shared-memory ring filled by cp.async.bulk (segbulk.cu);
+// 13 = the lean pass with the rows staged by TMA tile::gather4 (D = 128 sums; seglean.cu), everything else as 0.
 // Round 1's LDGSTS rings (2..4) and round 2's index-prefetch variants (6..9) were measured slower and removed
 // (profiles/r1_seg_variants.md, profiles/r2_seg_lean.md).
 int g_variant = 0;
@@ -307,8 +308,8 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
     }
     // the lean work-item kernel (seglean.cu) for rows of 128 / 256 / 512 floats
     int lean_rc = GNNB_EUNSUPPORTED;
-    if (g_variant == 0 || g_variant == 10) {
-        lean_rc = seg_reduce_lean(g, c, a, p.ws, g_variant == 0, st);
+    if (g_variant == 0 || g_variant == 10 || g_variant == 13) {
+        lean_rc = seg_reduce_lean(g, c, a, p.ws, g_variant != 10, st);
         if (lean_rc != GNNB_OK && lean_rc != GNNB_EUNSUPPORTED) return lean_rc;
     }
     if (lean_rc != GNNB_OK && (int64_t)c.nrows > 4 * g->E) {

@@ -249,6 +249,55 @@ class _GATAggregateFn(torch.autograd.Function):
         return dWx, del_, der, None, None
 
 
+class _GATCoreFn(torch.autograd.Function):
+    """The whole edge part of gat_conv for one projection Wx (N, H, C) and attention vector a (2C, H): per-node logit
+    halves (gnnb_gat_logit_terms, one pass over Wx), then the fused logits -> leakyrelu -> neighbourhood softmax ->
+    α-weighted sum (gnnb_gat_aggregate).  Backward: gnnb_gat_aggregate_bwd, then gnnb_gat_logit_terms_bwd adds the el / er
+    chain into dWx in place and reduces da — no (C,H,N) temporaries, no eager broadcast-multiply-reduce."""
+
+    @staticmethod
+    def forward(ctx, Wx_rows, a, plan, slope):
+        N, H, Cc = Wx_rows.shape
+        dev = Wx_rows.device
+        a_jl = a.detach().t().contiguous()                 # Julia (2C, H) column-major memory = rows (H, 2C)
+        el = torch.empty((N, H), dtype=torch.float32, device=dev)
+        er = torch.empty_like(el)
+        out = torch.empty_like(Wx_rows)
+        smax, ssum = torch.empty_like(el), torch.empty_like(el)
+        with torch.cuda.device(plan.device):
+            st = _stream(plan.device)
+            _lib.check(lib.gnnb_gat_logit_terms(Wx_rows.data_ptr(), a_jl.data_ptr(), N, Cc, H, el.data_ptr(), er.data_ptr(), st))
+            _lib.check(lib.gnnb_gat_aggregate(plan.h, Wx_rows.data_ptr(), el.data_ptr(), er.data_ptr(), Cc, H, slope,
+                                              out.data_ptr(), None, smax.data_ptr(), ssum.data_ptr(), st))
+        ctx.plan, ctx.slope, ctx.dims = plan, slope, (Cc, H)
+        ctx.save_for_backward(Wx_rows, a_jl, el, er, smax, ssum, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Wx_rows, a_jl, el, er, smax, ssum, out = ctx.saved_tensors
+        Cc, H = ctx.dims
+        N = Wx_rows.shape[0]
+        dout = dout.contiguous()
+        dWx = torch.empty_like(Wx_rows)
+        del_, der = torch.empty_like(el), torch.empty_like(er)
+        da_jl = torch.empty_like(a_jl)
+        with torch.cuda.device(ctx.plan.device):
+            st = _stream(ctx.plan.device)
+            _lib.check(lib.gnnb_gat_aggregate_bwd(ctx.plan.h, Wx_rows.data_ptr(), el.data_ptr(), er.data_ptr(), smax.data_ptr(),
+                                                  ssum.data_ptr(), out.data_ptr(), dout.data_ptr(), Cc, H, ctx.slope,
+                                                  dWx.data_ptr(), del_.data_ptr(), der.data_ptr(), st))
+            _lib.check(lib.gnnb_gat_logit_terms_bwd(Wx_rows.data_ptr(), a_jl.data_ptr(), del_.data_ptr(), der.data_ptr(), N, Cc,
+                                                    H, dWx.data_ptr(), da_jl.data_ptr(), st))
+        return dWx, da_jl.t(), None, None
+
+
+def gat_logit_fusable(chout: int, heads: int) -> bool:
+    """shapes csrc/gatlogit.cu covers: C/4 a power of two <= 32, C*H <= 4096 (config 3: 64 x 8)"""
+    g = chout // 4
+    return chout % 4 == 0 and g > 0 and (g & (g - 1)) == 0 and g <= 32 and chout * heads <= 4096 and (heads * 4 + chout // 4 - 1) // (chout // 4) <= 64
+
+
 def gat_fusable(chout: int, heads: int) -> bool:
     """Shapes the fused GAT kernels cover (csrc/gat.cu gat_shape): C/4 a power of two <= 32 (any number of heads), or
     C a power of two <= 32 with C*H <= 128.  Everything else takes the reference's own composition."""
@@ -302,9 +351,12 @@ def gat_conv(l, g: GNNGraph, x: torch.Tensor, e: Optional[torch.Tensor] = None, 
         plan = g.plan()
         Wr = _f32(rows(Wxj), plan.device)                       # (N, H, C)
         a = l.a                                                 # (2C, H)
-        el = (Wr * a[:chout, :].t().unsqueeze(0)).sum(-1)       # (N, H): rows 1..C pair with the target
-        er = (Wr * a[chout:, :].t().unsqueeze(0)).sum(-1)       # rows C+1..2C pair with the source
-        out = unrows(_GATAggregateFn.apply(Wr, el.contiguous(), er.contiguous(), plan, float(l.negative_slope)))
+        if gat_logit_fusable(chout, heads) and a.dtype == torch.float32 and Wr.data_ptr() % 16 == 0:
+            out = unrows(_GATCoreFn.apply(Wr, a, plan, float(l.negative_slope)))
+        else:
+            el = (Wr * a[:chout, :].t().unsqueeze(0)).sum(-1)   # (N, H): rows 1..C pair with the target
+            er = (Wr * a[chout:, :].t().unsqueeze(0)).sum(-1)   # rows C+1..2C pair with the source
+            out = unrows(_GATAggregateFn.apply(Wr, el.contiguous(), er.contiguous(), plan, float(l.negative_slope)))
     else:
         m = apply_edges(Fix1(gat_message, l), g, Wxi, Wxj, e)
         α = softmax_edge_neighbors(g, m["logα"])

@@ -187,6 +187,17 @@ int gnnb_gat_aggregate_bwd(gnnb_graph_t g, const float* Wx, const float* el, con
                            const float* dout, int64_t C, int64_t H, float slope, float* dWx, float* del,
                            float* der, void* stream);
 
+/* The per-node halves of the attention logits (csrc/gatlogit.cu) — replaces `sum(l.a .* vcat(Wxi, Wxj), dims = 1)` of
+ * gat_message (GNNlib/src/layers/conv.jl:157-163), which splits into a target and a source term:
+ *     el[h,i] = sum_c a[c,h] Wx[c,h,i]          er[h,j] = sum_c a[C+c,h] Wx[c,h,j]
+ * Wx (C,H,N), a (2C,H) column-major as the layer stores it, el / er (H,N).  One pass over Wx.
+ * Pullback: dWx_accum (C,H,N) += del[h,n] a[c,h] + der[h,n] a[C+c,h]  IN PLACE (it already holds the dWx of
+ * gnnb_gat_aggregate_bwd), da (2C,H) = [sum_n del Wx ; sum_n der Wx] — deterministic (fixed-order reduction).
+ * Shapes: C/4 a power of two <= 32, C*H <= 4096 (GNNB_EUNSUPPORTED otherwise). */
+int gnnb_gat_logit_terms(const float* Wx, const float* a, int64_t N, int64_t C, int64_t H, float* el, float* er, void* stream);
+int gnnb_gat_logit_terms_bwd(const float* Wx, const float* a, const float* del, const float* der, int64_t N, int64_t C,
+                             int64_t H, float* dWx_accum, float* da, void* stream);
+
 /* ------------------------------------------------------- dense layer part
  * replaces: l.σ.(weight * x .+ l.bias) of the conv layers (GNNlib/src/layers/conv.jl:39,69-71; :281) and its pullback.
  * A plain library GEMM like the reference's (BLAS/cuBLAS sgemm), issued through cuBLASLt 12.9 with the fp32-emulated
@@ -364,7 +375,8 @@ int gnnb_set_chunk_edges(int chunk);
  * 0 = default: the lean work-item kernel (csrc/seglean.cu), taking the plan's per-edge scale stream when there is one;
  * 10 = the lean kernel gathering cs[col] per edge;  12 = seg_reduce_kernel (the round-1 default: register-staged
  * LDG.128, 64-register cap);  5 = the same without the register cap;  1 = TMA-staged: one cp.async.bulk (UBLKCP) per
- * row into a shared-memory ring, mbarrier completion.  Measurements: profiles/r1_seg_variants.md, profiles/r2_seg_lean.md. */
+ * row into a shared-memory ring, mbarrier completion;  13 = the lean pass with rows staged by TMA tile::gather4 (four
+ * indexed rows per request into a per-warp shared-memory ring; D = 128 sums).  Measurements: profiles/r1_seg_variants.md, profiles/r2_seg_lean.md. */
 int gnnb_set_kernel_variant(int v);
 
 #ifdef __cplusplus

@@ -29,12 +29,12 @@ for chunk in CHUNKS:
         row = {"chunk": chunk, "variant": v}
         for tr in (0, 1):
             for _ in range(2):
-                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, None if v == 0 else c.data_ptr(), D, out.data_ptr(), None))
+                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, None if v in (0, 13) else c.data_ptr(), D, out.data_ptr(), None))
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
             torch.cuda.synchronize()
             for a, b in evs:
                 a.record()
-                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, None if v == 0 else c.data_ptr(), D, out.data_ptr(), None))
+                gnn._lib.check(lib.gnnb_gcn_propagate(g2.plan().h, tr, x.data_ptr(), None, None if v in (0, 13) else c.data_ptr(), D, out.data_ptr(), None))
                 b.record()
             torch.cuda.synchronize()
             row["fwd_ms" if tr == 0 else "bwd_ms"] = sum(a.elapsed_time(b) for a, b in evs) / 5

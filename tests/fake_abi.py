@@ -327,6 +327,27 @@ class FakeLib:
         _arr(der, (p.ns, H))[...] = _segment(SUM, dz, p.s, p.ns)
         return OK
 
+    def gnnb_gat_logit_terms(self, Wx, a, N, Cc, H, el, er, stream):
+        self.calls.append("gnnb_gat_logit_terms")
+        W = _arr(Wx, (N, H, Cc)).astype(np.float64)
+        A = _arr(a, (H, 2 * Cc)).astype(np.float64)          # Julia (2C, H) column-major memory
+        _arr(el, (N, H))[...] = (W * A[None, :, :Cc]).sum(-1)
+        _arr(er, (N, H))[...] = (W * A[None, :, Cc:]).sum(-1)
+        return OK
+
+    def gnnb_gat_logit_terms_bwd(self, Wx, a, del_, der, N, Cc, H, dWx, da, stream):
+        self.calls.append("gnnb_gat_logit_terms_bwd")
+        W = _arr(Wx, (N, H, Cc)).astype(np.float64)
+        A = _arr(a, (H, 2 * Cc)).astype(np.float64)
+        dl = _arr(del_, (N, H)).astype(np.float64)
+        dr = _arr(der, (N, H)).astype(np.float64)
+        acc = _arr(dWx, (N, H, Cc))
+        acc[...] = acc.astype(np.float64) + dl[:, :, None] * A[None, :, :Cc] + dr[:, :, None] * A[None, :, Cc:]
+        out = _arr(da, (H, 2 * Cc))
+        out[:, :Cc] = (dl[:, :, None] * W).sum(0)
+        out[:, Cc:] = (dr[:, :, None] * W).sum(0)
+        return OK
+
     # ------------------------------------------------------------------ node-partitioned shards
     def gnnb_gather_rows(self, idx, n, x, D, out, stream):
         self.calls.append("gnnb_gather_rows")
