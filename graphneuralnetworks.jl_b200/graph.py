@@ -124,12 +124,16 @@ class GNNGraph:
     def __init__(self, s, t=None, w=None, *, num_nodes: Optional[int] = None, ndata=None, edata=None,
                  gdata=None, num_graphs: int = 1, graph_indicator=None, device=None):
         if t is None:
-            if isinstance(s, (tuple, list)) and len(s) in (2, 3) and not np.isscalar(s[0]):
+            as_edges = isinstance(s, tuple) and len(s) in (2, 3)           # (s, t) / (s, t, w): tuples
+            if not as_edges and isinstance(s, list) and len(s) in (2, 3) and all(hasattr(v, "__len__") for v in s):
+                # a nested list is an adjacency matrix when it is square ([[0,1],[1,0]]), a list of index vectors otherwise
+                as_edges = not all(len(v) == len(s) for v in s)
+            if as_edges:
                 if len(s) == 3:
                     s, t, w = s
                 else:
                     s, t = s
-            else:  # adjacency matrix: A[i,j] != 0 <=> edge i -> j  (convert.jl:86-100, column-major findnz order)
+            else:  # adjacency matrix: A[i,j] != 0 <=> edge i -> j  (convert.jl:75-95, column-major findnz order)
                 A = s if isinstance(s, torch.Tensor) else torch.as_tensor(np.asarray(s))
                 if A.dim() != 2 or A.shape[0] != A.shape[1]:
                     raise ValueError("adjacency matrix must be square")
@@ -137,8 +141,7 @@ class GNNGraph:
                 t, s = nz[:, 0] + 1, nz[:, 1] + 1
                 if num_nodes is None:
                     num_nodes = A.shape[0]
-                if A.is_floating_point() and not bool(((A == 0) | (A == 1)).all()):
-                    w = A.t()[A.t() != 0].to(torch.float32)
+                w = A.t()[A.t() != 0].to(torch.float32)        # v = A[nz] always travels as the edge weight (convert.jl:85)
         self.s = _as_index(s, device)
         self.t = _as_index(t, device)
         assert self.s.dim() == 1 and self.s.shape == self.t.shape, "s and t must be vectors of equal length"
