@@ -110,6 +110,8 @@ _SIGS = {
     "gnnb_sample_positions_host": (_int, [_i32, _i64, _int, C.c_uint64, C.c_uint64, _vp, _i64, C.POINTER(_i64)]),
     "gnnb_propagate_host": (_int, [_vp, _int, _int, _int, _f32p, _f32p, _i64, _f32p]),
     "gnnb_gcn_propagate_host": (_int, [_vp, _int, _f32p, _f32p, _i64, _f32p]),
+    "gnnb_linear2": (_int, [_f32p, _f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _i64, _f32p, _vp]),
+    "gnnb_linear2_bwd": (_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _f32p, _vp]),
     "gnnb_gat_logit_terms": (_int, [_f32p, _f32p, _i64, _i64, _i64, _f32p, _f32p, _vp]),
     "gnnb_gat_logit_terms_bwd": (_int, [_f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _f32p, _f32p, _vp]),
     "gnnb_gcn_conv_step_host": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

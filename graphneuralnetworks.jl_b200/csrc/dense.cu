@@ -112,6 +112,8 @@ static int matmul(cublasOperation_t ta, cublasOperation_t tb, int64_t m, int64_t
 
 int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, int64_t M, int64_t K, int64_t Nout, float* y,
                   cudaStream_t st);   // dense_tc.cu
+int linear_tf32x3_ex(const float* x, const float* W, int64_t ldw, const float* bias, const float* addend, int relu, int64_t M,
+                     int64_t K, int64_t Nout, float* y, cudaStream_t st);
 int linear_tf32x3_error();
 int dw_tf32x3(const float* dpre, const float* x, int64_t M, int64_t Din, int64_t Dout, float* dW, cudaStream_t st);
 extern int g_tc_enabled;
@@ -119,6 +121,15 @@ extern int g_tc_enabled;
 __global__ void transpose_small_kernel(const float* __restrict__ w, int rows, int cols, float* __restrict__ wt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * cols) { const int r = i / cols, c = i % cols; wt[(size_t)c * rows + r] = w[i]; }
+}
+// the same for a column block of a wider matrix (row stride ld), and the inverse copy of a block into such a matrix
+__global__ void transpose_block_kernel(const float* __restrict__ w, int rows, int cols, int ld, float* __restrict__ wt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) { const int r = i / cols, c = i % cols; wt[(size_t)c * rows + r] = w[(size_t)r * ld + c]; }
+}
+__global__ void place_block_kernel(const float* __restrict__ blk, int rows, int cols, int ld, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) { const int r = i / cols, c = i % cols; out[(size_t)r * ld + c] = blk[i]; }
 }
 
 // dpre = dy * (y > 0) (relu pullback, y = forward output) or dpre = dy; partial column sums per block for db
@@ -188,6 +199,66 @@ int gnnb_linear(const float* x, const float* W, const float* bias, int relu, int
     }
     // column-major: Y(Dout x N) = W(Dout x Din) X(Din x N); W is stored (Dout, Din) row-major = col-major (Din x Dout)
     return lt::matmul(CUBLAS_OP_T, CUBLAS_OP_N, Dout, N, Din, W, Din, x, Din, y, Dout, bias, relu, (cudaStream_t)stream);
+}
+
+// σ.(W * vcat(x1, x2) .+ b) without the vcat: the two column blocks of W hit x1 and x2 in two accumulating passes of the
+// tcgen05 kernel (the second adds the first's result before the activation).  sage_conv, conv.jl:281.
+int gnnb_linear2(const float* x1, const float* x2, const float* W, const float* bias, int relu, int64_t N, int64_t Din1,
+                 int64_t Din2, int64_t Dout, float* y, void* stream) {
+    if (N < 0 || Din1 <= 0 || Din2 <= 0 || Dout <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
+    if (N == 0) return GNNB_OK;
+    if (!x1 || !x2 || !W || !y) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ld = Din1 + Din2;
+    int rc = linear_tf32x3_ex(x1, W, ld, nullptr, nullptr, 0, N, Din1, Dout, y, st);
+    if (rc == GNNB_EUNSUPPORTED) GNNB_FAIL(GNNB_EUNSUPPORTED, "linear2: both input widths must be multiples of 32 <= 128, Dout a multiple of 16 <= 128, 16 B-aligned operands");
+    if (rc != GNNB_OK) return rc;
+    rc = linear_tf32x3_ex(x2, W + Din1, ld, bias, y, relu, N, Din2, Dout, y, st);
+    if (rc == GNNB_EUNSUPPORTED) GNNB_FAIL(GNNB_EUNSUPPORTED, "linear2: unsupported second block");
+    return rc;
+}
+
+int gnnb_linear2_bwd(const float* dy, const float* y, const float* x1, const float* x2, const float* W, int relu, int64_t N,
+                     int64_t Din1, int64_t Din2, int64_t Dout, float* dpre_ws, float* dx1, float* dx2, float* dW, float* db,
+                     void* stream) {
+    if (N < 0 || Din1 <= 0 || Din2 <= 0 || Dout <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ld = Din1 + Din2;
+    if (N == 0) {
+        if (dW) GNNB_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)(ld * Dout), st));
+        if (db) GNNB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Dout, st));
+        return GNNB_OK;
+    }
+    if (!dy || !W || !x1 || !x2) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
+    if (relu && (!y || !dpre_ws)) GNNB_FAIL(GNNB_EINVAL, "relu pullback needs the forward output and a (N,Dout) workspace");
+    if (Dout != 128 || Din1 % 32 || Din2 % 32 || Din1 > 128 || Din2 > 128)
+        GNNB_FAIL(GNNB_EUNSUPPORTED, "linear2_bwd: Dout must be 128 and both input widths multiples of 32 <= 128");
+    // dpre = dy .* (y > 0), db: one pass (gnnb_linear_bwd's own, with no GEMM outputs requested)
+    const float* dpre = dy;
+    if (relu || db) {
+        GNNB_TRY(gnnb_linear_bwd(dy, y, nullptr, W, relu, N, Din1, Dout, dpre_ws, nullptr, nullptr, db, stream));
+        if (relu) dpre = dpre_ws;
+    }
+    static float* tmp = nullptr;                       // 128x128 transposed block / dW block
+    if (!tmp) GNNB_CUDA(cudaMalloc(&tmp, sizeof(float) * 128 * 128));
+    for (int blk = 0; blk < 2; ++blk) {
+        const int64_t Din = blk ? Din2 : Din1;
+        const float* Wb = W + (blk ? Din1 : 0);
+        float* dx = blk ? dx2 : dx1;
+        if (dx) {                                      // dx = dpre * W_block
+            transpose_block_kernel<<<(unsigned)ceil_div(Dout * Din, 256), 256, 0, st>>>(Wb, (int)Dout, (int)Din, (int)ld, tmp);
+            GNNB_LAUNCHED();
+            const int rc = linear_tf32x3(dpre, tmp, nullptr, 0, N, Dout, Din, dx, st);
+            if (rc != GNNB_OK) { if (rc == GNNB_EUNSUPPORTED) GNNB_FAIL(GNNB_EUNSUPPORTED, "linear2_bwd: dx shape not covered"); return rc; }
+        }
+        if (dW) {                                      // dW_block = dpre' * x_block, placed into its columns of dW
+            const int rc = dw_tf32x3(dpre, blk ? x2 : x1, N, Din, Dout, tmp, st);
+            if (rc != GNNB_OK) { if (rc == GNNB_EUNSUPPORTED) GNNB_FAIL(GNNB_EUNSUPPORTED, "linear2_bwd: dW shape not covered"); return rc; }
+            place_block_kernel<<<(unsigned)ceil_div(Dout * Din, 256), 256, 0, st>>>(tmp, (int)Dout, (int)Din, (int)ld, dW + (blk ? Din1 : 0));
+            GNNB_LAUNCHED();
+        }
+    }
+    return GNNB_OK;
 }
 
 int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, int relu, int64_t N, int64_t Din,

@@ -89,11 +89,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 struct Params {
     const float* __restrict__ x;     // [M][K]
-    const float* __restrict__ w;     // [Nout][K]
+    const float* __restrict__ w;     // [Nout][ldw]: row n holds its K coefficients at w + n*ldw
     const float* __restrict__ bias;  // [Nout] or null
+    const float* __restrict__ addend;  // [M][Nout] or null: y = act(x W^T + bias + addend) (may alias y)
     float* __restrict__ y;           // [M][Nout]
     int64_t M;
-    int K, Nout, relu;
+    int K, Nout, relu, ldw;
     int* err;
 };
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
         const int kv = p.K >> 2;                               // float4 per row of W
         for (int idx = tid; idx < p.Nout * kv; idx += THREADS) {
             const int n = idx / kv, c4 = idx - n * kv, kb = c4 >> 3, c = c4 & 7;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.K) + c4);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.ldw) + c4);
             const float4 b = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
             const float4 s = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
             const int off = kb * KBLK_BYTES + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4);
@@ -231,7 +232,6 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
                     o.y = __uint_as_float(r[j + 1]) + sbias[c0 + j + 1];
                     o.z = __uint_as_float(r[j + 2]) + sbias[c0 + j + 2];
                     o.w = __uint_as_float(r[j + 3]) + sbias[c0 + j + 3];
-                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = o;
                 }
                 __syncwarp();
@@ -239,9 +239,16 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = (lane >> 3) + 4 * i;
-                    const float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + f);
-                    if (row0 + rr < p.M && c0 + f < p.Nout)
-                        *reinterpret_cast<float4*>(p.y + (size_t)(row0 + rr) * p.Nout + c0 + f) = o;
+                    float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + f);
+                    if (row0 + rr < p.M && c0 + f < p.Nout) {
+                        const size_t at = (size_t)(row0 + rr) * p.Nout + c0 + f;
+                        if (p.addend) {
+                            const float4 a = *reinterpret_cast<const float4*>(p.addend + at);
+                            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                        }
+                        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4*>(p.y + at) = o;
+                    }
                 }
                 __syncwarp();
             }
@@ -455,11 +462,18 @@ static int* g_tc_err = nullptr;
 int g_tc_enabled = 1;
 
 // returns GNNB_EUNSUPPORTED (no error text) when the shape is not covered by the tensor-core kernel
+int linear_tf32x3_ex(const float* x, const float* W, int64_t ldw, const float* bias, const float* addend, int relu, int64_t M,
+                     int64_t K, int64_t Nout, float* y, cudaStream_t st);
 int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, int64_t M, int64_t K, int64_t Nout, float* y,
                   cudaStream_t st) {
+    return linear_tf32x3_ex(x, W, K, bias, nullptr, relu, M, K, Nout, y, st);
+}
+// W rows `ldw` floats apart (a column block of a wider matrix); addend (M, Nout) added before the activation
+int linear_tf32x3_ex(const float* x, const float* W, int64_t ldw, const float* bias, const float* addend, int relu, int64_t M,
+                     int64_t K, int64_t Nout, float* y, cudaStream_t st) {
     if (!g_tc_enabled) return GNNB_EUNSUPPORTED;
-    if (K % 32 != 0 || K > 128 || Nout % 16 != 0 || Nout > 128 || Nout < 16) return GNNB_EUNSUPPORTED;
-    if (((uintptr_t)x & 15) || ((uintptr_t)W & 15) || ((uintptr_t)y & 15)) return GNNB_EUNSUPPORTED;
+    if (K % 32 != 0 || K > 128 || Nout % 16 != 0 || Nout > 128 || Nout < 16 || ldw % 4 != 0 || ldw < K) return GNNB_EUNSUPPORTED;
+    if (((uintptr_t)x & 15) || ((uintptr_t)W & 15) || ((uintptr_t)y & 15) || ((uintptr_t)addend & 15)) return GNNB_EUNSUPPORTED;
     if (M == 0) return GNNB_OK;
     static bool configured = false;
     static int nsm = 0;
@@ -473,7 +487,8 @@ int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, i
         configured = true;
     }
     tc::Params p;
-    p.x = x; p.w = W; p.bias = bias; p.y = y; p.M = M; p.K = (int)K; p.Nout = (int)Nout; p.relu = relu; p.err = g_tc_err;
+    p.x = x; p.w = W; p.bias = bias; p.addend = addend; p.y = y; p.M = M; p.K = (int)K; p.Nout = (int)Nout; p.relu = relu;
+    p.ldw = (int)ldw; p.err = g_tc_err;
     const int64_t ntiles = ceil_div(M, tc::BM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
     tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(p);

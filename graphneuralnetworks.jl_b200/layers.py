@@ -409,6 +409,42 @@ class GATConv(torch.nn.Module):
 
 
 # ------------------------------------------------------------------------------------------ SAGEConv
+class _Linear2Fn(torch.autograd.Function):
+    """σ.(W * vcat(x1, x2) .+ b) for σ ∈ {identity, relu} through gnnb_linear2 / gnnb_linear2_bwd: the two column blocks
+    of W meet x1 and x2 in two accumulating passes of the tcgen05 kernel — no (Din1+Din2, N) vcat temporary."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, W, bias, relu_flag):
+        N, D1 = x1.shape
+        D2 = x2.shape[1]
+        Dout = W.shape[0]
+        y = torch.empty((N, Dout), dtype=torch.float32, device=x1.device)
+        Wc = W.contiguous()
+        with torch.cuda.device(x1.device):
+            _lib.check(lib.gnnb_linear2(x1.data_ptr(), x2.data_ptr(), Wc.data_ptr(), None if bias is None else bias.data_ptr(),
+                                        int(relu_flag), N, D1, D2, Dout, y.data_ptr(), _stream(x1.device)))
+        ctx.relu_flag, ctx.has_bias = bool(relu_flag), bias is not None
+        ctx.save_for_backward(x1, x2, Wc, y if relu_flag else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1, x2, W, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        N, D1 = x1.shape
+        D2, Dout = x2.shape[1], W.shape[0]
+        dx1 = torch.empty_like(x1) if ctx.needs_input_grad[0] else None
+        dx2 = torch.empty_like(x2) if ctx.needs_input_grad[1] else None
+        dW = torch.empty_like(W) if ctx.needs_input_grad[2] else None
+        db = torch.empty(Dout, dtype=torch.float32, device=dy.device) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
+        ws = torch.empty_like(dy) if ctx.relu_flag else None
+        p = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(dy.device):
+            _lib.check(lib.gnnb_linear2_bwd(dy.data_ptr(), p(y), x1.data_ptr(), x2.data_ptr(), W.data_ptr(), int(ctx.relu_flag), N,
+                                            D1, D2, Dout, p(ws), p(dx1), p(dx2), p(dW), p(db), _stream(dy.device)))
+        return dx1, dx2, dW, db, None
+
+
 def sage_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
     """GNNlib/src/layers/conv.jl:277-283: σ.(W * vcat(xi, propagate(copy_xj, g, aggr, xj)) .+ b).
     W is (out, 2·in): its first `in` columns multiply x_i, the rest the aggregated neighbours."""
@@ -416,7 +452,14 @@ def sage_conv(l, g: GNNGraph, x: torch.Tensor) -> torch.Tensor:
     xj, xi = expand_srcdst(g, x)
     m = propagate(copy_xj, g, l.aggr, xj=xj)
     W = l.weight
-    xm = unrows(torch.cat([rows(xi), rows(m)], dim=1))        # vcat(xi, m): (2·in, N)
+    sig, b = _sigma(l), _bias(l)
+    r1, r2 = rows(xi), rows(m)
+    D1, D2, Dout = r1.shape[1], r2.shape[1], W.shape[0]
+    if (r1.is_cuda and r1.dtype == torch.float32 and W.dtype == torch.float32 and Dout == 128 and D1 % 32 == 0 and D2 % 32 == 0
+            and D1 <= 128 and D2 <= 128 and (sig is identity or _is_relu(sig))):
+        # the two column blocks of W in two accumulating tcgen05 passes: no vcat temporary
+        return unrows(_Linear2Fn.apply(r1.contiguous(), r2.contiguous(), W, None if b is None else b.contiguous(), _is_relu(sig)))
+    xm = unrows(torch.cat([r1, r2], dim=1))                   # vcat(xi, m): (2·in, N)
     return _linear(l, W, xm, True)                            # σ.(W * vcat(xi, m) .+ b): one GEMM, bias/σ in the epilogue
 
 

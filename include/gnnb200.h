@@ -200,9 +200,9 @@ int gnnb_gat_logit_terms_bwd(const float* Wx, const float* a, const float* del, 
 
 /* ------------------------------------------------------- dense layer part
  * replaces: l.σ.(weight * x .+ l.bias) of the conv layers (GNNlib/src/layers/conv.jl:39,69-71; :281) and its pullback.
- * A plain library GEMM like the reference's (BLAS/cuBLAS sgemm), issued through cuBLASLt 12.9 with the fp32-emulated
- * compute type (3 x bf16 split, bf16 tensor cores, fp32 accumulate; SIMT sgemm if unavailable), bias (+relu) in the
- * epilogue.  x (Din,N), W (Dout,Din) row-major as the layer stores it, bias NULL or Dout floats, y (Dout,N).
+ * Din, Dout <= 128: hand-written tcgen05 kernels (csrc/dense_tc.cu: 3xTF32 split, TMEM accumulators, bias/relu epilogue
+ * written as whole row segments); every other shape: a library GEMM like the reference's, issued through cuBLASLt 12.9
+ * with the fp32-emulated compute type (bf16 x9, fp32 accumulate; SIMT sgemm if unavailable), bias (+relu) in the epilogue.  x (Din,N), W (Dout,Din) row-major as the layer stores it, bias NULL or Dout floats, y (Dout,N).
  * relu: 0 = identity, 1 = relu. */
 int gnnb_linear(const float* x, const float* W, const float* bias, int relu, int64_t N, int64_t Din,
                 int64_t Dout, float* y, void* stream);
@@ -211,6 +211,16 @@ int gnnb_linear(const float* x, const float* W, const float* bias, int relu, int
  * gradient are one hand-written pass (deterministic two-stage column sum). */
 int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, int relu, int64_t N,
                     int64_t Din, int64_t Dout, float* dpre_ws, float* dx, float* dW, float* db, void* stream);
+/* σ.(W * vcat(x1, x2) .+ b) — sage_conv's dense part (GNNlib/src/layers/conv.jl:281) — without the (Din1+Din2, N) vcat
+ * temporary: the two column blocks of W (Dout, Din1+Din2, row-major as the layer stores it) meet x1 (Din1,N) and x2 (Din2,N)
+ * in two passes of the tcgen05 kernel, the second adding the first's result before bias / activation.  Pullback: dx1, dx2,
+ * dW (Dout, Din1+Din2), db, each may be NULL.  Shapes: Din1, Din2 multiples of 32 <= 128, Dout = 128 (forward also Dout a
+ * multiple of 16 <= 128); GNNB_EUNSUPPORTED otherwise (callers concatenate and use gnnb_linear). */
+int gnnb_linear2(const float* x1, const float* x2, const float* W, const float* bias, int relu, int64_t N, int64_t Din1,
+                 int64_t Din2, int64_t Dout, float* y, void* stream);
+int gnnb_linear2_bwd(const float* dy, const float* y, const float* x1, const float* x2, const float* W, int relu, int64_t N,
+                     int64_t Din1, int64_t Din2, int64_t Dout, float* dpre_ws, float* dx1, float* dx2, float* dW, float* db,
+                     void* stream);
 /* 1 (default) = try the fp32-emulated tensor-core GEMM; 0 = force the SIMT sgemm.  *_active: -1 not yet used,
  * 0 unavailable / off, 1 in use. */
 int gnnb_dense_set_emulation(int on);

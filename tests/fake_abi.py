@@ -327,6 +327,33 @@ class FakeLib:
         _arr(der, (p.ns, H))[...] = _segment(SUM, dz, p.s, p.ns)
         return OK
 
+    def gnnb_linear2(self, x1, x2, W, bias, relu, N, Din1, Din2, Dout, y, stream):
+        self.calls.append("gnnb_linear2")
+        Wm = _arr(W, (Dout, Din1 + Din2)).astype(np.float64)
+        pre = _arr(x1, (N, Din1)).astype(np.float64) @ Wm[:, :Din1].T + _arr(x2, (N, Din2)).astype(np.float64) @ Wm[:, Din1:].T
+        if bias is not None:
+            pre = pre + _arr(bias, (Dout,)).astype(np.float64)
+        _arr(y, (N, Dout))[...] = np.maximum(pre, 0) if relu else pre
+        return OK
+
+    def gnnb_linear2_bwd(self, dy, y, x1, x2, W, relu, N, Din1, Din2, Dout, dpre_ws, dx1, dx2, dW, db, stream):
+        self.calls.append("gnnb_linear2_bwd")
+        Wm = _arr(W, (Dout, Din1 + Din2)).astype(np.float64)
+        dpre = _arr(dy, (N, Dout)).astype(np.float64)
+        if relu:
+            dpre = dpre * (_arr(y, (N, Dout)) > 0)
+        if dx1 is not None:
+            _arr(dx1, (N, Din1))[...] = dpre @ Wm[:, :Din1]
+        if dx2 is not None:
+            _arr(dx2, (N, Din2))[...] = dpre @ Wm[:, Din1:]
+        if dW is not None:
+            out = _arr(dW, (Dout, Din1 + Din2))
+            out[:, :Din1] = dpre.T @ _arr(x1, (N, Din1)).astype(np.float64)
+            out[:, Din1:] = dpre.T @ _arr(x2, (N, Din2)).astype(np.float64)
+        if db is not None:
+            _arr(db, (Dout,))[...] = dpre.sum(0)
+        return OK
+
     def gnnb_gat_logit_terms(self, Wx, a, N, Cc, H, el, er, stream):
         self.calls.append("gnnb_gat_logit_terms")
         W = _arr(Wx, (N, H, Cc)).astype(np.float64)

@@ -951,3 +951,36 @@ def test_gat_logit_terms_c_abi(gnn, Cc, H, n):
     da_ref = torch.cat([(dl.double()[:, :, None] * W64).sum(0), (dr.double()[:, :, None] * W64).sum(0)], dim=1)   # (H, 2C)
     assert float((outs[0][0].double() - dWx_ref).norm() / dWx_ref.norm()) < 2e-6
     assert float((outs[0][1].double() - da_ref).norm() / da_ref.norm()) < 5e-6
+
+
+@pytest.mark.parametrize("N,D1,D2", [(70001, 128, 128), (5000, 96, 32), (129, 128, 64)])
+@pytest.mark.parametrize("relu_flag,with_bias", [(1, True), (0, False)])
+def test_linear2_c_abi(gnn, N, D1, D2, relu_flag, with_bias):
+    """gnnb_linear2 / gnnb_linear2_bwd — σ.(W * vcat(x1, x2) .+ b) as two accumulating tcgen05 passes over the column blocks
+    of W (sage_conv, conv.jl:281) — against float64."""
+    lib = gnn._lib.lib
+    Dout = 128
+    gen = torch.Generator(device="cuda").manual_seed(N + D1)
+    x1 = torch.randn(N, D1, device="cuda", generator=gen)
+    x2 = torch.randn(N, D2, device="cuda", generator=gen)
+    W = torch.randn(Dout, D1 + D2, device="cuda", generator=gen) / (D1 + D2) ** 0.5
+    b = torch.randn(Dout, device="cuda", generator=gen) if with_bias else None
+    dy = torch.randn(N, Dout, device="cuda", generator=gen)
+    y = torch.empty(N, Dout, device="cuda")
+    gnn._lib.check(lib.gnnb_linear2(x1.data_ptr(), x2.data_ptr(), W.data_ptr(), None if b is None else b.data_ptr(), relu_flag,
+                                    N, D1, D2, Dout, y.data_ptr(), None))
+    pre = torch.cat([x1, x2], 1).double() @ W.double().t() + (0 if b is None else b.double())
+    ref = pre.clamp(min=0) if relu_flag else pre
+    assert rel(y.cpu(), ref.cpu()) < 5e-6
+    ws = torch.empty_like(dy); dx1 = torch.empty_like(x1); dx2 = torch.empty_like(x2)
+    dW = torch.empty_like(W); db = torch.empty(Dout, device="cuda")
+    gnn._lib.check(lib.gnnb_linear2_bwd(dy.data_ptr(), y.data_ptr(), x1.data_ptr(), x2.data_ptr(), W.data_ptr(), relu_flag, N, D1,
+                                        D2, Dout, ws.data_ptr(), dx1.data_ptr(), dx2.data_ptr(), dW.data_ptr(),
+                                        db.data_ptr() if with_bias else None, None))
+    dpre = dy.double() * (y > 0) if relu_flag else dy.double()
+    assert rel(dx1.cpu(), (dpre @ W.double()[:, :D1]).cpu()) < 5e-6
+    assert rel(dx2.cpu(), (dpre @ W.double()[:, D1:]).cpu()) < 5e-6
+    assert rel(dW.cpu(), (dpre.t() @ torch.cat([x1, x2], 1).double()).cpu()) < 5e-6
+    if with_bias:
+        assert rel(db.cpu(), dpre.sum(0).cpu()) < 5e-6
+    assert lib.gnnb_dense_tc_error() == 0

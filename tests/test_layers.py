@@ -520,6 +520,33 @@ def test_agnn_conv(gnn, be):
 
 
 # ------------------------------------------------------------------------------------------------ generic path, readout
+@pytest.mark.parametrize("sig", ["relu", "identity"])
+def test_sage_conv_split_weight_path(gnn, be, sig):
+    """SAGEConv 128 -> 128 on a CUDA device takes gnnb_linear2 (the CPU test double keeps the vcat formula): the two column blocks of W meet x_i and the aggregated neighbours in two
+    accumulating tcgen05 passes instead of a (2·in, N) vcat + one GEMM (conv.jl:281); output, dx, dW, db against float64."""
+    rng = np.random.default_rng(11)
+    dev = be.dev
+    g, R, s, t = make_graph(gnn, rng, dev)
+    D = 128
+    x = rng.standard_normal((R.n, D))
+    xt, xr = jl(gnn, x, dev, True), r64(x, True)
+    m = R.propagate(xr, "mean")
+    act = torch.relu if sig == "relu" else gnn.layers.identity
+    layer = gnn.SAGEConv(D, D, act, device=dev)
+    setp(rng, layer.bias)
+    out = layer(g, xt)
+    W64, b64 = p64(layer.weight).requires_grad_(True), p64(layer.bias).requires_grad_(True)
+    pre = torch.cat([xr, m], dim=1) @ W64.t() + b64
+    ref = torch.relu(pre) if sig == "relu" else pre
+    assert rel(gnn.rows(out), ref) < 2e-6 * be.tol
+    cot = torch.randn(ref.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    if sig == "relu":                                        # keep away from the kink: relu' is discontinuous at 0
+        cot = cot * (pre.detach().abs() > 1e-4)
+    gx, gW, gb = torch.autograd.grad((gnn.rows(out).double() * cot.to(out.device)).sum(), [xt, layer.weight, layer.bias])
+    rx, rW, rb = torch.autograd.grad((ref * cot).sum(), [xr, W64, b64])
+    assert rel(gnn.rows(gx), rx) < 2e-5 * be.tol and rel(gW, rW) < 2e-5 * be.tol and rel(gb, rb) < 2e-5 * be.tol
+
+
 def test_generic_messages_with_structures(gnn, be):
     """apply_edges / aggregate_neighbors over dict, tuple and None containers (GNNGraphs/src/gatherscatter.jl:1-18)"""
     rng = np.random.default_rng(11)
