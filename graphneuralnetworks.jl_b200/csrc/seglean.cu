@@ -262,27 +262,39 @@ __global__ void __launch_bounds__(256, 4) seg_lean_kernel(const LeanParams p) {
 // held by loads in flight), all lanes wait on the stage's mbarrier (complete_tx) and reduce the four rows with LDS.128.
 // A stage is refilled with the NEXT batch's rows as soon as it has been consumed.  Same items, same arithmetic order:
 // bit-identical to the register-staged kernel.
-constexpr int G4_WARPS = 8, G4_STAGES = 8, G4_STAGE_BYTES = 4 * 512;
+// Rows of KV*128 floats: a group of four edges is one request of 4 x 512 B (KV = 1), 4 x 1 KB (KV = 2) or two requests of
+// 4 x 1 KB on one barrier (KV = 4: a TMA box is at most 256 elements wide).  128 KB of ring per CTA in every case.
+template <int KV> struct G4 {
+    static constexpr int WARPS = KV == 4 ? 4 : 8;
+    static constexpr int STAGES = KV == 1 ? 8 : 4;                // groups in flight per warp
+    static constexpr int REQS = KV == 4 ? 2 : 1;                  // gather4 requests per group
+    static constexpr int BOX_COLS = KV * 128 / REQS;
+    static constexpr int ROW_BYTES = KV * 512;
+    static constexpr int STAGE_BYTES = 4 * ROW_BYTES;
+    static constexpr int SMEM = WARPS * STAGES * STAGE_BYTES + WARPS * STAGES * 8;
+};
 
-template <int SMODE>
-__global__ void __launch_bounds__(G4_WARPS * 32, 1) seg_gather4_kernel(const LeanParams p, const __grid_constant__ CUtensorMap map) {
+template <int KV, int SMODE>
+__global__ void __launch_bounds__(G4<KV>::WARPS * 32, 1) seg_gather4_kernel(const LeanParams p, const __grid_constant__ CUtensorMap map) {
+    using C = G4<KV>;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int S = C::STAGES;
+    constexpr int64_t STRIDE = (int64_t)KV * 128;
     extern __shared__ __align__(1024) unsigned char g4smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* ring = g4smem + warp * (G4_STAGES * G4_STAGE_BYTES);
+    unsigned char* ring = g4smem + warp * (S * C::STAGE_BYTES);
     const uint32_t ring_u = tma::smem_u32(ring);
-    const uint32_t bar0 = tma::smem_u32(g4smem + G4_WARPS * G4_STAGES * G4_STAGE_BYTES) + warp * G4_STAGES * 8;
+    const uint32_t bar0 = tma::smem_u32(g4smem + C::WARPS * S * C::STAGE_BYTES) + warp * S * 8;
     if (lane == 0) {
-        for (int s = 0; s < G4_STAGES; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < S; ++s) tma::mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma::fence_proxy_async();
     }
     __syncwarp();
     uint32_t par = 0;                                  // parity of every stage's next completion
-    const float4* rowl = reinterpret_cast<const float4*>(ring) + lane;     // this lane's 16 B of row 0 of stage 0
 
-    // four rows of group q of a batch whose gathered nodes sit in `c` (nv valid edges): issued by lane 0
-    auto issue = [&](int q, int c, int nv) {
+    // the four rows of group q (edges 4q .. 4q+3) of a batch whose gathered nodes sit in `c` (nv valid edges) into stage st
+    auto issue = [&](int st, int q, int c, int nv) {
         const int last = nv - 1;
         const int k = 4 * q;
         const int c0 = __shfl_sync(FULL, c, k <= last ? k : last);
@@ -291,12 +303,15 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 1) seg_gather4_kernel(const Lea
         const int c3 = __shfl_sync(FULL, c, k + 3 <= last ? k + 3 : last);
         if (lane == 0) {
             tma::fence_proxy_async();                  // the stage was read through the generic proxy
-            tma::mbar_expect_tx(bar0 + 8 * q, G4_STAGE_BYTES);
-            tma::gather4(ring_u + q * G4_STAGE_BYTES, &map, 0, c0, c1, c2, c3, bar0 + 8 * q);
+            tma::mbar_expect_tx(bar0 + 8 * st, C::STAGE_BYTES);
+#pragma unroll
+            for (int rq = 0; rq < C::REQS; ++rq)       // request rq lands its 4 x BOX_COLS block after the previous one
+                tma::gather4(ring_u + st * C::STAGE_BYTES + rq * (4 * C::BOX_COLS * 4), &map, rq * C::BOX_COLS, c0, c1, c2, c3,
+                             bar0 + 8 * st);
         }
     };
 
-    for (int item = blockIdx.x * G4_WARPS + warp; item < p.n_items; item += gridDim.x * G4_WARPS) {
+    for (int item = blockIdx.x * C::WARPS + warp; item < p.n_items; item += gridDim.x * C::WARPS) {
         const int4 it = __ldg(p.items + item);
         const int e_end = it.y;
         const bool partial = __any_sync(FULL, it.z >= 0);
@@ -311,17 +326,19 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 1) seg_gather4_kernel(const Lea
                 if (SMODE == 2) s1 = __ldg(p.cs + c);
             }
         };
-        float4 acc = f4(0.f);
+        float4 acc[KV];
+#pragma unroll
+        for (int i = 0; i < KV; ++i) acc[i] = f4(0.f);
         int e = it.x;
         int c_n, r_n; float s1_n; bool last_n;
         load_lane(e, c_n, r_n, s1_n, last_n);
         {
             const int nv = (e_end - e) < 32 ? (e_end - e) : 32;
-            for (int q = 0; 4 * q < nv; ++q) issue(q, c_n, nv);
+            for (int q = 0; q < S && 4 * q < nv; ++q) issue(q, q, c_n, nv);
         }
         bool more = true;
         while (more) {
-            const int r_l = r_n;
+            const int c_l = c_n, r_l = r_n;
             const float s1_l = s1_n;
             const unsigned vmask = __ballot_sync(FULL, e + lane < e_end);
             const unsigned bmask = partial ? 0u : __ballot_sync(FULL, last_n);
@@ -329,37 +346,80 @@ __global__ void __launch_bounds__(G4_WARPS * 32, 1) seg_gather4_kernel(const Lea
             if (!partial && e + lane < e_end && p.ct) sc_l = __ldg(p.ct + r_l);
             more = __any_sync(FULL, e + 32 < e_end);
             if (more) load_lane(e + 32, c_n, r_n, s1_n, last_n);
+            const int nv = (e_end - e) < 32 ? (e_end - e) : 32;
             const int nn = more ? ((e_end - e - 32) < 32 ? (e_end - e - 32) : 32) : 0;
 #pragma unroll 1
-            for (int q = 0; q < 8 && (vmask >> (4 * q)) != 0u; ++q) {
-                const uint32_t bar = bar0 + 8 * q;
-                const uint32_t ph = (par >> q) & 1u;
+            for (int q = 0; q < 8 && 4 * q < nv; ++q) {
+                const int st = q % S;                  // 8 groups per batch, S divides 8: the stage of group q
+                const uint32_t bar = bar0 + 8 * st;
+                const uint32_t ph = (par >> st) & 1u;
                 {   // bounded: a request that never completes aborts the kernel instead of hanging the GPU
                     uint32_t spin = 0;
                     while (!tma::mbar_try(bar, ph)) { if (++spin > (1u << 24)) __trap(); }
                 }
-                par ^= 1u << q;
-                const float4* src = rowl + q * (G4_STAGE_BYTES / 16);
+                par ^= 1u << st;
+                const unsigned char* sbase = ring + st * C::STAGE_BYTES;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = 4 * q + u;
                     const float s1 = (SMODE != 0) ? __shfl_sync(FULL, s1_l, j) : 1.f;
-                    if ((vmask >> j) & 1u) acc = lcomb<SMODE, false, AG_SUM>(acc, src[u * 32], s1, 1.f, 1.f);
+                    if ((vmask >> j) & 1u) {
+#pragma unroll
+                        for (int i = 0; i < KV; ++i) {
+                            // float f = i*128 + lane*4 of row u: request f / BOX_COLS, inside it row u, column f % BOX_COLS
+                            const int f = i * 128 + lane * 4;
+                            const float4 v = *reinterpret_cast<const float4*>(sbase + (f / C::BOX_COLS) * (4 * C::BOX_COLS * 4) +
+                                                                              u * (C::BOX_COLS * 4) + (f % C::BOX_COLS) * 4);
+                            acc[i] = lcomb<SMODE, false, AG_SUM>(acc[i], v, s1, 1.f, 1.f);
+                        }
+                    }
                     if ((bmask >> j) & 1u) {
                         const int rj = __shfl_sync(FULL, r_l, j);
                         const float sc = __shfl_sync(FULL, sc_l, j);
-                        *reinterpret_cast<float4*>(p.out + (int64_t)rj * 128 + lane * 4) =
-                            make_float4(acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc);
-                        acc = f4(0.f);
+#pragma unroll
+                        for (int i = 0; i < KV; ++i) {
+                            *reinterpret_cast<float4*>(p.out + (int64_t)rj * STRIDE + i * 128 + lane * 4) =
+                                make_float4(acc[i].x * sc, acc[i].y * sc, acc[i].z * sc, acc[i].w * sc);
+                            acc[i] = f4(0.f);
+                        }
                     }
                 }
                 __syncwarp();                          // every lane is done with the stage
-                if (4 * q < nn) issue(q, c_n, nn);     // refill it with the next batch's rows
+                // refill it with the group S ahead: of this batch, or of the next one
+                if (q + S < 8) { if (4 * (q + S) < nv) issue(st, q + S, c_l, nv); }
+                else if (4 * (q + S - 8) < nn) issue(st, q + S - 8, c_n, nn);
             }
             e += 32;
         }
-        if (partial) *reinterpret_cast<float4*>(p.ws + (int64_t)it.z * 128 + lane * 4) = acc;
+        if (partial) {
+#pragma unroll
+            for (int i = 0; i < KV; ++i) *reinterpret_cast<float4*>(p.ws + (int64_t)it.z * STRIDE + i * 128 + lane * 4) = acc[i];
+        }
     }
+}
+
+template <int KV>
+int launch_gather4(const LeanParams& p, int smode, const float* x, int32_t ncols, cudaStream_t st) {
+    using C = G4<KV>;
+    CUtensorMap map;
+    if (tma::make_map_2d_f32(&map, x, (uint64_t)ncols, (uint64_t)KV * 128, (uint64_t)C::ROW_BYTES, C::BOX_COLS, 1) != 0)
+        GNNB_FAIL(GNNB_ECUDA, "cuTensorMapEncodeTiled failed for the gather4 variant");
+    static int nsm = 0;
+    if (!nsm) {
+        int dev = 0;
+        GNNB_CUDA(cudaGetDevice(&dev));
+        GNNB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<KV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<KV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<KV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    }
+    const int64_t want = ceil_div((int64_t)p.n_items, C::WARPS);
+    const unsigned blocks = (unsigned)(want < nsm ? want : nsm);
+    if (smode == 0) seg_gather4_kernel<KV, 0><<<blocks, C::WARPS * 32, C::SMEM, st>>>(p, map);
+    else if (smode == 1) seg_gather4_kernel<KV, 1><<<blocks, C::WARPS * 32, C::SMEM, st>>>(p, map);
+    else seg_gather4_kernel<KV, 2><<<blocks, C::WARPS * 32, C::SMEM, st>>>(p, map);
+    GNNB_LAUNCHED();
+    return GNNB_OK;
 }
 
 template <int KV, int SMODE, bool HAS_W, int HALO, int AGG>
@@ -482,27 +542,10 @@ int seg_reduce_lean(gnnb_graph* g, const Csr& c, const SegArgs& a, float* ws, bo
     p.sign = (a.aggr == GNNB_MIN) ? -1.f : 1.f;
     if (p.n_items == 0) return GNNB_OK;
     const int use_halo = halo ? 1 : 0;
-    if (g_variant == 13 && a.D == 128 && agg == AG_SUM && !halo && a.w == nullptr) {
-        CUtensorMap map;
-        if (tma::make_map_2d_f32(&map, a.x, (uint64_t)c.ncols, 128, 512, 128, 1) != 0)
-            GNNB_FAIL(GNNB_ECUDA, "cuTensorMapEncodeTiled failed for the gather4 variant");
-        const size_t smem = (size_t)G4_WARPS * G4_STAGES * G4_STAGE_BYTES + G4_WARPS * G4_STAGES * 8;
-        static int nsm = 0;
-        if (!nsm) {
-            int dev = 0;
-            GNNB_CUDA(cudaGetDevice(&dev));
-            GNNB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-            GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GNNB_CUDA(cudaFuncSetAttribute(seg_gather4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        int64_t want = ceil_div((int64_t)p.n_items, G4_WARPS);
-        const unsigned blocks = (unsigned)(want < nsm ? want : nsm);
-        if (smode == 0) seg_gather4_kernel<0><<<blocks, G4_WARPS * 32, smem, st>>>(p, map);
-        else if (smode == 1) seg_gather4_kernel<1><<<blocks, G4_WARPS * 32, smem, st>>>(p, map);
-        else seg_gather4_kernel<2><<<blocks, G4_WARPS * 32, smem, st>>>(p, map);
-        GNNB_LAUNCHED();
-        return GNNB_OK;
+    if (g_variant == 13 && agg == AG_SUM && !halo && a.w == nullptr) {      // rows staged by TMA tile::gather4 (A/B variant)
+        if (a.D == 128) return launch_gather4<1>(p, smode, a.x, c.ncols, st);
+        if (a.D == 256) return launch_gather4<2>(p, smode, a.x, c.ncols, st);
+        return launch_gather4<4>(p, smode, a.x, c.ncols, st);
     }
     int rc;
     if (a.D == 128) rc = launch_lean1<1>(p, smode, a.w != nullptr, use_halo, agg, st);
