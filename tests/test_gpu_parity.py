@@ -629,7 +629,7 @@ def test_tma_staged_variant_large_chunks(gnn, oracle, variant):
 @pytest.mark.parametrize("D", [128, 256, 512])
 @pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
 def test_lean_kernel_is_bit_identical(graph, oracle, gnn, variant, D, aggr):
-    """The work-item kernel (seglean.cu, variants 0 / 10) against seg_reduce_kernel (variant 12): same bits for every message /
+    """The work-item kernel (seglean.cu, variants 0 / 10, and 13 = its TMA gather4 staging) against seg_reduce_kernel (variant 12): same bits for every message /
     aggregation / scale combination, and both against the oracle."""
     name, s, t, n, g = graph
     lib = gnn._lib.lib
@@ -655,7 +655,7 @@ def test_lean_kernel_is_bit_identical(graph, oracle, gnn, variant, D, aggr):
     variant(12)
     base = run()
     assert rel(np_rows(base[0]), oracle.propagate_unfused(aggr, s, t, n, np_rows(x).astype(np.float64))) < TOL
-    for v in (0, 10):
+    for v in (0, 10, 13):                # 13: rows staged by TMA tile::gather4 (plain / node-scaled sums; the rest as 0)
         variant(v)
         for i, (a, b) in enumerate(zip(run(), base)):
             assert torch.equal(a, b), f"variant {v} case {i}"
@@ -679,7 +679,7 @@ def test_lean_kernel_gcn_plan_norm_and_chunks(gnn, oracle, variant, D):
             c = gnn.layers._gcn_c(g2)
             xr = torch.as_tensor(x).cuda()
             outs = {}
-            for v, cp in ((12, c), (10, c), (0, c), (0, None), (12, None)):
+            for v, cp in ((12, c), (10, c), (0, c), (0, None), (13, None), (13, c), (12, None)):
                 variant(v)
                 for tr in (0, 1):
                     out = torch.empty(n, D, device="cuda")
