@@ -824,8 +824,8 @@ def run_ours(args):
         if args.config not in (2, 5):
             raise SystemExit("configs 1, 3, 4 are single-GPU workloads")
         from gnnb200 import partition
-        if args.config == 5 and "GNNB_HALO_SLICES" not in os.environ:
-            os.environ["GNNB_HALO_SLICES"] = "4"     # 1 KB rows: the halo buffers only fit beside the features in column slices
+        if args.config == 5 and "GNNB_HALO_BUFFERS" not in os.environ:
+            os.environ["GNNB_HALO_BUFFERS"] = "1"    # 1 KB rows: one halo buffer per shard (forward and backward alternate)
         return partition.bench_multi(args, world, int(os.environ.get("RANK", "0")), dev, SEED, ClockSampler, measured_peaks,
                                      cpu_leg=None if args.no_cpu else (lambda: cpu_leg_gcn(args)[0]))
     if args.config == 5:

@@ -703,8 +703,9 @@ int gnnb_gat_aggregate(gnnb_graph_t g, const float* Wx, const float* el, const f
     if (!Wx || !el || !er || !out || !seg_max || !seg_sum) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
     int vec, kk;
     if (!gat_shape(C, H, Wx, out, &vec, &kk))
-        GNNB_FAIL(GNNB_EUNSUPPORTED, "fused GAT needs C*H <= 512 with C/4 a power of two <= 32 (or C a power of two <= 32, C*H <= 128); "
-                                     "use the generic apply_edges/softmax_edge_neighbors/aggregate_neighbors composition");
+        GNNB_FAIL(GNNB_EUNSUPPORTED, "fused GAT needs C/4 a power of two <= 32 with 16 B-aligned Wx / out (any number of heads), or C a "
+                                     "power of two <= 32 with C*H <= 128; use the generic apply_edges/softmax_edge_neighbors/"
+                                     "aggregate_neighbors composition");
     cudaStream_t st = (cudaStream_t)stream;
     GNNB_TRY(ensure_csr(g, false, st));
     const Csr& c = g->by_dst;

@@ -350,8 +350,10 @@ def gat_conv(l, g: GNNGraph, x: torch.Tensor, e: Optional[torch.Tensor] = None, 
     if fused and e is None and xi is xj and gat_fusable(chout, heads) and float(getattr(l, "dropout", 0.0) or 0.0) == 0.0:
         plan = g.plan()
         Wr = _f32(rows(Wxj), plan.device)                       # (N, H, C)
+        if Wr.data_ptr() % 16 != 0:                             # a misaligned view: the fused kernels take 16 B-aligned rows
+            Wr = Wr.clone()
         a = l.a                                                 # (2C, H)
-        if gat_logit_fusable(chout, heads) and a.dtype == torch.float32 and Wr.data_ptr() % 16 == 0:
+        if gat_logit_fusable(chout, heads) and a.dtype == torch.float32:
             out = unrows(_GATCoreFn.apply(Wr, a, plan, float(l.negative_slope)))
         else:
             el = (Wr * a[:chout, :].t().unsqueeze(0)).sum(-1)   # (N, H): rows 1..C pair with the target

@@ -330,10 +330,14 @@ class DistGraph:
         all_recv = [None] * world
         dist.all_gather_object(all_recv, list(shard.recv_counts), group=self.group)
         row0 = [int(sum(all_recv[q][:rank])) for q in range(world)]   # where my rows start in every peer's halo buffer
+        # double buffer: pass k+1 never overwrites what a slower rank's pass k still reads.  GNNB_HALO_BUFFERS=1 is safe when
+        # passes over a shard alternate with passes over the other one (one layer, forward / backward: the other pass's
+        # completion collective orders them) and halves the memory — what config 5's 1 KB rows need
+        nbuf = 1 if os.environ.get("GNNB_HALO_BUFFERS", "2") == "1" else 2
         bufs, handles = [], []
         try:
             with torch.cuda.device(dev):
-                for _ in range(2):                               # double buffer: pass k+1 never overwrites what pass k reads
+                for _ in range(nbuf):
                     ptr = C.c_void_p()
                     _lib.check(lib.gnnb_dev_alloc(C.byref(ptr), max(shard.n_halo, 1) * D * 4))
                     h = (C.c_ubyte * 64)()
@@ -342,16 +346,16 @@ class DistGraph:
                     handles.append(bytes(h))
         except Exception:
             ok = 0
-            handles = [bytes(64), bytes(64)]
+            handles = [bytes(64)] * nbuf
         all_handles = [None] * world
         dist.all_gather_object(all_handles, handles, group=self.group)
-        peer_ptrs = [[0] * world, [0] * world]
+        peer_ptrs = [[0] * world for _ in range(nbuf)]
         try:
             with torch.cuda.device(dev):
                 for q in range(world):
                     if q == rank or shard.send_counts[q] == 0:
                         continue
-                    for b in range(2):
+                    for b in range(nbuf):
                         pp = C.c_void_p()
                         hb = (C.c_ubyte * 64).from_buffer_copy(all_handles[q][b])
                         _lib.check(lib.gnnb_ipc_open_handle(hb, C.byref(pp)))
@@ -368,7 +372,8 @@ class DistGraph:
         for q in range(world):
             seg.append(seg[-1] + int(shard.send_counts[q]))
         st = {"bufs": bufs, "row0": (C.c_int64 * world)(*row0), "seg": (C.c_int64 * (world + 1))(*seg),
-              "peer_c": [(C.c_void_p * world)(*[C.c_void_p(v) for v in peer_ptrs[b]]) for b in range(2)], "turn": 0,
+              "peer_c": [(C.c_void_p * world)(*[C.c_void_p(v) for v in peer_ptrs[b]]) for b in range(nbuf)], "turn": 0,
+              "nbuf": nbuf,
               "peer_ptrs": peer_ptrs,
               "flag": torch.zeros(1, device=dev)}
         shard.push[D] = st
@@ -415,7 +420,7 @@ class DistGraph:
             self._keep = t
             return t.data_ptr()
         b = st["turn"]
-        st["turn"] ^= 1
+        st["turn"] = (b + 1) % st["nbuf"]
         with torch.cuda.device(self.device):
             _lib.check(lib.gnnb_halo_push(shard.send_idx.data_ptr(), st["seg"], st["peer_c"][b], st["row0"], self.world,
                                           x_rows.data_ptr(), D, _stream(self.device)))
@@ -548,12 +553,15 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_
     # the fused kernel alone on this rank's forward shard (CUDA events on the launch stream), max over ranks
     c, cf, cb = dg.gcn_c()
     xr = gnn.rows(x.detach())
-    halo = dg.halo(dg.fwd, xr)
+    x.grad = None
+    layer.weight.grad = None
+    torch.cuda.empty_cache()
+    hp = dg.halo_ptr(dg.fwd, xr)                        # the halo rows where the step's own exchange puts them
     out = torch.empty_like(xr)
     st = torch.cuda.current_stream(dev).cuda_stream
 
     def kern():
-        _lib.check(lib.gnnb_propagate_halo(dg.fwd.plan.h, _lib.COPY_XJ, _lib.SUM, xr.data_ptr(), halo.data_ptr(),
+        _lib.check(lib.gnnb_propagate_halo(dg.fwd.plan.h, _lib.COPY_XJ, _lib.SUM, xr.data_ptr(), hp if dg.fwd.n_halo else None,
                                            dg.n_local, None, cf.data_ptr(), c.data_ptr(), D, out.data_ptr(), st))
 
     for _ in range(3):
