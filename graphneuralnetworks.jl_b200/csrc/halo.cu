@@ -7,33 +7,38 @@
 namespace gnnb {
 
 constexpr int MAX_PEERS = 16;
+constexpr int PUSH_ROWS = 256;       // rows of one peer's segment a CTA walks through, 8 at a time (one per warp)
 struct PushParams {
     float* peer_base[MAX_PEERS];     // halo buffer of every peer (peer-mapped), nullptr for self / unused
     int64_t peer_row0[MAX_PEERS];    // first row inside that buffer that belongs to this rank
     int64_t seg_start[MAX_PEERS + 1];  // send list is grouped by peer: rows [seg_start[p], seg_start[p+1]) go to peer p
-    int64_t stride;                  // multiplicative permutation of the row order (coprime with n_send): every rank writes
-                                     // to all of its peers at the same time instead of peer after peer (all ranks hammering
-                                     // rank 0's inbound links first: measured 395 GB/s at 4 GPUs)
     int world;
 };
 
-// one warp per row: the lanes copy the row as float4 (or float) pieces; the destination is a peer's halo buffer
+// blockIdx.x = peer, blockIdx.y = chunk of PUSH_ROWS consecutive rows of that peer's segment: CTAs are scheduled x-fastest,
+// so a rank feeds all of its peers at once (all ranks hammering rank 0's inbound links first measured 395 GB/s at 4 GPUs),
+// while every peer's buffer is written in ascending order by a moving front of a few hundred 8-row windows.  Round 1 /
+// early round 2 visited the rows in a pseudo-random order instead: fine for 512 B rows, but at 1 KB rows the scattered
+// remote writes fell off a translation cliff (halo_probe: 675 / 566 / 128 GB/s at D = 64 / 128 / 256 with 1.6 M rows).
 template <int VEC>
-__global__ void __launch_bounds__(256) halo_push_kernel(const PushParams pp, const int32_t* __restrict__ send_idx, int64_t n_send,
+__global__ void __launch_bounds__(256) halo_push_kernel(const PushParams pp, const int32_t* __restrict__ send_idx,
                                                         const float* __restrict__ x, int64_t D) {
-    const int lane = threadIdx.x & 31;
-    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (v >= n_send) return;
-    const int64_t r = (int64_t)(((uint64_t)v * (uint64_t)pp.stride) % (uint64_t)n_send);   // stride < 2^25, v < 2^31
-    int p = 0;
-    while (p + 1 < pp.world && r >= pp.seg_start[p + 1]) ++p;       // <= 16 peers: a short scan
-    float* dst = pp.peer_base[p] + (size_t)(pp.peer_row0[p] + (r - pp.seg_start[p])) * D;
-    const float* src = x + (size_t)__ldg(send_idx + r) * D;
-    if (VEC == 4) {
-        for (int64_t f = (int64_t)lane * 4; f < D; f += 128)
-            *reinterpret_cast<float4*>(dst + f) = __ldg(reinterpret_cast<const float4*>(src + f));
-    } else {
-        for (int64_t f = lane; f < D; f += 32) dst[f] = __ldg(src + f);
+    const int p = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t seg0 = pp.seg_start[p], len = pp.seg_start[p + 1] - seg0;
+    float* const base = pp.peer_base[p] + (size_t)pp.peer_row0[p] * D;
+    for (int64_t c = blockIdx.y; c * PUSH_ROWS < len; c += gridDim.y) {
+        const int64_t k1 = (c + 1) * PUSH_ROWS < len ? (c + 1) * PUSH_ROWS : len;
+        for (int64_t k = c * PUSH_ROWS + warp; k < k1; k += 8) {
+            float* dst = base + (size_t)k * D;
+            const float* src = x + (size_t)__ldg(send_idx + seg0 + k) * D;
+            if (VEC == 4) {
+                for (int64_t f = (int64_t)lane * 4; f < D; f += 128)
+                    *reinterpret_cast<float4*>(dst + f) = __ldg(reinterpret_cast<const float4*>(src + f));
+            } else {
+                for (int64_t f = lane; f < D; f += 32) dst[f] = __ldg(src + f);
+            }
+        }
     }
 }
 
@@ -92,16 +97,19 @@ int gnnb_halo_push(const int32_t* send_idx_dev, const int64_t* seg_start_host, c
     const int64_t n_send = seg_start_host[world];
     if (n_send == 0) return GNNB_OK;
     if (!send_idx_dev || !x) GNNB_FAIL(GNNB_EINVAL, "halo_push: NULL argument");
-    pp.stride = 1;
-    for (int64_t cand : {1000003LL, 999983LL, 15485863LL, 32452843LL}) {
-        if (n_send % cand != 0) { pp.stride = cand % n_send; break; }   // prime not dividing n_send => bijection mod n_send
+    int64_t max_seg = 0;
+    for (int p = 0; p < world; ++p) {
+        const int64_t l = seg_start_host[p + 1] - seg_start_host[p];
+        if (l > max_seg) max_seg = l;
     }
-    if (pp.stride == 0) pp.stride = 1;
     cudaStream_t st = (cudaStream_t)stream;
     bool v4 = D % 4 == 0 && !((uintptr_t)x & 15);
     for (int p = 0; p < world; ++p) if ((uintptr_t)pp.peer_base[p] & 15) v4 = false;
-    if (v4) halo_push_kernel<4><<<(unsigned)ceil_div(n_send, 8), 256, 0, st>>>(pp, send_idx_dev, n_send, x, D);
-    else halo_push_kernel<1><<<(unsigned)ceil_div(n_send, 8), 256, 0, st>>>(pp, send_idx_dev, n_send, x, D);
+    int64_t chunks = ceil_div(max_seg, PUSH_ROWS);
+    if (chunks > 65535) chunks = 65535;                          // the kernel strides over the rest
+    const dim3 grid((unsigned)world, (unsigned)chunks);
+    if (v4) halo_push_kernel<4><<<grid, 256, 0, st>>>(pp, send_idx_dev, x, D);
+    else halo_push_kernel<1><<<grid, 256, 0, st>>>(pp, send_idx_dev, x, D);
     GNNB_LAUNCHED();
     return GNNB_OK;
 }

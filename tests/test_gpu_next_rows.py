@@ -104,3 +104,67 @@ def test_reparameterised_layers(gnn, oracle):
     alpha = oracle.softmax_edge_neighbors(t2, n, 1.5 * cos)
     ref = oracle.scatter("+", alpha * x64[s2 - 1], t2, n)
     assert rel(gnn.rows(gnn.agnn_conv(l, g, xt)).cpu(), ref) < 1e-5
+
+
+# ------------------------------------------------------------------ node-partition shards built on the device (csrc/shard.cu)
+@pytest.mark.parametrize("world,ownership", [(2, "contiguous"), (3, "cyclic"), (4, "balanced")])
+def test_shard_builder_matches_the_torch_restatement(gnn, oracle, world, ownership):
+    """gnnb_shard_builder_* (chunked, stable compaction, sort + unique halo, renaming, self loops, plan) for every rank of a
+    `world`, on one GPU, against partition.build_shard (torch on CPU): halo lists, request counts and the plan's CSR
+    (rowptr, col, eid) must be identical integers.  Needs no process group."""
+    import ctypes as C
+    from gnnb200 import partition as P
+    lib = gnn._lib.lib
+    rng = np.random.default_rng(world)
+    n, E = 997, 20000
+    s = np.minimum((rng.random(E) ** 3 * n).astype(np.int64), n - 1) + 1          # skewed: low ids are hubs
+    t = np.minimum((rng.random(E) ** 2 * n).astype(np.int64), n - 1) + 1
+    sd, td = torch.as_tensor(s).cuda(), torch.as_tensor(t).cuda()
+    s0, t0 = torch.as_tensor(s) - 1, torch.as_tensor(t) - 1
+    relabel = relabel_dev = None
+    if ownership == "balanced":
+        cost = torch.zeros(n, dtype=torch.int32, device="cuda")
+        relabel_dev = torch.empty(n, dtype=torch.int32, device="cuda")
+        order = torch.empty(n, dtype=torch.int32, device="cuda")
+        gnn._lib.check(lib.gnnb_degree_accumulate(sd.data_ptr(), td.data_ptr(), E, 8, 1, n, cost.data_ptr(), None))
+        gnn._lib.check(lib.gnnb_balanced_relabel(cost.data_ptr(), n, world, relabel_dev.data_ptr(), order.data_ptr(), None))
+        deg = torch.bincount(s0, minlength=n) + torch.bincount(t0, minlength=n)
+        assert torch.equal(cost.cpu().long(), deg)
+        by_degree = torch.sort(deg, descending=True, stable=True).indices
+        pos = torch.arange(n)
+        r, j = pos // world, pos % world
+        o = torch.where((r % 2 == 1) & (r < n // world), world - 1 - j, j)
+        relabel = torch.empty(n, dtype=torch.int32)
+        relabel[by_degree] = (r * world + o).to(torch.int32)
+        assert torch.equal(relabel_dev.cpu(), relabel)
+        assert torch.equal(order.cpu().long()[relabel.long()], pos)
+    bounds = [0, 100, 400, n][:world] + [n] if ownership == "contiguous" else None
+    first = P.ownership_first(n, world, ownership, bounds)
+    ps, pt = P.to_pid(s0, world, first, ownership, relabel), P.to_pid(t0, world, first, ownership, relabel)
+    for rank in range(world):
+        b = C.c_void_p()
+        barr = (C.c_int64 * (world + 1))(*first) if ownership == "contiguous" else None
+        gnn._lib.check(lib.gnnb_shard_builder_create(C.byref(b), n, world, rank, 0 if ownership == "contiguous" else 1, barr,
+                                                     None if relabel_dev is None else relabel_dev.data_ptr()))
+        try:
+            for a in range(0, E, 7001):                                               # ragged chunks
+                gnn._lib.check(lib.gnnb_shard_builder_add(b, sd[a:a + 7001].data_ptr(), td[a:a + 7001].data_ptr(),
+                                                          min(7001, E - a), 8, 1, None))
+            for direction, (key0, other0) in enumerate(((pt, ps), (ps, pt))):
+                ref = P.build_shard(key0, other0, first[rank], first[rank + 1], first, True)
+                h = C.c_void_p()
+                nl, nh, ne = C.c_int64(), C.c_int64(), C.c_int64()
+                rc = (C.c_int64 * world)()
+                gnn._lib.check(lib.gnnb_shard_builder_finish(b, direction, 1, C.byref(h), C.byref(nl), C.byref(nh), C.byref(ne), rc, None))
+                plan = gnn.graph._Plan(h.value, torch.device("cuda"))
+                assert (nl.value, nh.value, ne.value) == (ref["n_local"], ref["halo"].numel(), ref["row"].numel())
+                assert list(rc) == ref["recv_counts"]
+                hl = torch.empty(max(nh.value, 1), dtype=torch.int32, device="cuda")
+                gnn._lib.check(lib.gnnb_shard_builder_halo(b, direction, hl.data_ptr(), None))
+                assert torch.equal(hl[:nh.value].cpu(), ref["halo_local"])
+                rowptr, col, eid = np.empty(nl.value + 1, np.int32), np.empty(ne.value, np.int32), np.empty(ne.value, np.int32)
+                gnn._lib.check(lib.gnnb_graph_csr(plan.h, 0, rowptr.ctypes.data, col.ctypes.data, eid.ctypes.data, None))
+                rp_ref, col_ref, perm_ref = oracle.csr(ref["row"].numpy() + 1, ref["col"].numpy() + 1, nl.value)
+                assert np.array_equal(rowptr, rp_ref) and np.array_equal(col, col_ref) and np.array_equal(eid, perm_ref)
+        finally:
+            lib.gnnb_shard_builder_destroy(b)
