@@ -68,6 +68,23 @@ def graph(request, gnn):
     return request.param, s, t, kw["n"], g
 
 
+@pytest.fixture(scope="module", params=[k for k in GRAPHS if k != "sparse"])
+def graph_with_edges(request, gnn):
+    """the graphs whose targets mostly have in-edges (GAT always runs with self loops; `sparse` adds nothing there)"""
+    rng = np.random.default_rng(list(GRAPHS).index(request.param))
+    kw = GRAPHS[request.param]
+    s, t = make_graph(rng, **kw)
+    return request.param, s, t, kw["n"], gnn.GNNGraph(s, t, num_nodes=kw["n"]).to("cuda")
+
+
+@pytest.fixture(scope="module")
+def small_graph(gnn):
+    rng = np.random.default_rng(0)
+    kw = GRAPHS["small"]
+    s, t = make_graph(rng, **kw)
+    return "small", s, t, kw["n"], gnn.GNNGraph(s, t, num_nodes=kw["n"]).to("cuda")
+
+
 # ------------------------------------------------------------------------------------------ index work
 def test_csr_bit_exact(graph, oracle, gnn):
     _, s, t, n, g = graph
@@ -142,12 +159,8 @@ def test_rmat_gpu_equals_cpu(gnn, oracle):
 
 
 # ---------------------------------------------------------------------------------------- fused propagate
-@pytest.mark.parametrize("D", [1, 3, 7, 10, 16, 20, 64, 128, 132, 256, 512, 300, 1433])
-@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
-def test_propagate_copy_xj(graph, oracle, gnn, D, aggr):
+def _check_propagate_copy_xj(graph, oracle, gnn, D, aggr):
     name, s, t, n, g = graph
-    if D > 300 and name != "small":
-        pytest.skip("wide rows only on the small graph")
     rng = np.random.default_rng(D)
     x = rng.standard_normal((n, D)).astype(np.float32)
     got = np_rows(gnn.propagate(gnn.copy_xj, g, aggr, xj=jl(x)))
@@ -157,6 +170,18 @@ def test_propagate_copy_xj(graph, oracle, gnn, D, aggr):
         assert (got == oracle.propagate_unfused(aggr, s, t, n, x)).all()
     elif name in ("small", "empty_rows", "sparse"):   # rows <= chunk: same summation order as NNlib's CPU scatter
         assert (got == oracle.propagate_unfused(aggr, s, t, n, x)).all()
+
+
+@pytest.mark.parametrize("D", [1, 3, 7, 10, 16, 20, 64, 128, 132, 256, 300])
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+def test_propagate_copy_xj(graph, oracle, gnn, D, aggr):
+    _check_propagate_copy_xj(graph, oracle, gnn, D, aggr)
+
+
+@pytest.mark.parametrize("D", [512, 1433])
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+def test_propagate_copy_xj_wide_rows(small_graph, oracle, gnn, D, aggr):
+    _check_propagate_copy_xj(small_graph, oracle, gnn, D, aggr)
 
 
 @pytest.mark.parametrize("D", [1, 5, 16, 128, 260])
@@ -377,11 +402,19 @@ def test_gcn_closed_form_and_conv_weight(gnn):
 
 
 @pytest.mark.parametrize("din,dout", [(3, 5), (16, 7), (128, 128), (40, 16)])
-@pytest.mark.parametrize("loops", [True, False])
-def test_gcn_conv_parity_and_grad(graph, oracle, gnn, din, dout, loops):
+def test_gcn_conv_parity_and_grad(graph, oracle, gnn, din, dout):
+    _check_gcn_conv_parity_and_grad(graph, oracle, gnn, din, dout, True)
+
+
+@pytest.mark.parametrize("din,dout", [(3, 5), (16, 7), (128, 128), (40, 16)])
+def test_gcn_conv_parity_and_grad_without_self_loops(small_graph, oracle, gnn, din, dout):
+    """without self loops isolated nodes give c = Inf (the reference tests skip such graphs too): the small graph, with
+    every node made a target once"""
+    _check_gcn_conv_parity_and_grad(small_graph, oracle, gnn, din, dout, False)
+
+
+def _check_gcn_conv_parity_and_grad(graph, oracle, gnn, din, dout, loops):
     name, s, t, n, g = graph
-    if not loops and name != "small":
-        pytest.skip("without self loops isolated nodes give c=Inf (the reference tests skip them too)")
     rng = np.random.default_rng(din)
     if not loops:   # make every node a target at least once
         s = np.concatenate([s, np.arange(1, n + 1)]); t = np.concatenate([t, np.roll(np.arange(1, n + 1), 1)])
@@ -485,10 +518,8 @@ def _gat_reference_bwd(oracle, s, t, n, Wx, el, er, dout, slope):
 
 @pytest.mark.parametrize("Cc,H", [(64, 8), (16, 4), (8, 2), (4, 1), (32, 2), (128, 1), (128, 4), (2, 3), (1, 4), (16, 1), (32, 4), (64, 4),
                                   (16, 8), (4, 32)])
-def test_gat_aggregate_c_abi(graph, oracle, gnn, Cc, H):
-    name, s, t, n, g = graph
-    if name == "sparse":
-        pytest.skip("GAT always runs with self loops: no empty targets")
+def test_gat_aggregate_c_abi(graph_with_edges, oracle, gnn, Cc, H):
+    name, s, t, n, g = graph_with_edges
     lib = gnn._lib.lib
     rng = np.random.default_rng(Cc * 10 + H)
     s2, t2 = oracle.add_self_loops(s, t, n)
@@ -533,12 +564,10 @@ def test_gat_unsupported_shape_is_loud(gnn):
 @pytest.mark.parametrize("din,chout", [(3, 5), (8, 16), (16, 64)])
 @pytest.mark.parametrize("heads", [1, 2])
 @pytest.mark.parametrize("concat", [True, False])
-def test_gat_conv_layer(graph, oracle, gnn, din, chout, heads, concat):
+def test_gat_conv_layer(graph_with_edges, oracle, gnn, din, chout, heads, concat):
     """GraphNeuralNetworks/test/layers/conv.jl:154-170 (heads x concat sweep): output size, fused == the reference's
     own composition (generic gather/softmax/scatter path), gradients of both paths agree, forward ≈ fp64 oracle."""
-    name, s, t, n, g = graph
-    if name == "sparse":
-        pytest.skip("covered by the other graphs")
+    name, s, t, n, g = graph_with_edges
     torch.manual_seed(0)
     l = gnn.GATConv(din, chout, torch.relu, heads=heads, concat=concat, device="cuda")
     with torch.no_grad():
