@@ -168,3 +168,44 @@ def test_shard_builder_matches_the_torch_restatement(gnn, oracle, world, ownersh
                 assert np.array_equal(rowptr, rp_ref) and np.array_equal(col, col_ref) and np.array_equal(eid, perm_ref)
         finally:
             lib.gnnb_shard_builder_destroy(b)
+
+
+@pytest.mark.parametrize("relu_flag,with_bias,bwd", [(1, True, True), (0, False, True), (1, True, False)])
+def test_gcn_conv_step_host_entry(gnn, oracle, relu_flag, with_bias, bwd):
+    """gnnb_gcn_conv_step_host — a whole GCNConv forward (+ backward) on HOST arrays through the C ABI, the call bench.py times
+    as e2e — against the oracle composition in fp64 (forward) and against the device-side layer (bit for bit: same kernels)."""
+    lib = gnn._lib.lib
+    n, E, D = 3000, 40000, 128
+    rng = np.random.default_rng(7)
+    s, t = oracle.rmat(n, E, 17)
+    g = gnn.GNNGraph(s, t, num_nodes=n).cuda()
+    g2 = gnn.add_self_loops(g)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    dy = rng.standard_normal((n, D)).astype(np.float32)
+    W = (rng.standard_normal((D, D)) / np.sqrt(D)).astype(np.float32)
+    b = rng.standard_normal(D).astype(np.float32)
+    y, dx, dW, db = np.empty_like(x), np.empty_like(x), np.empty_like(W), np.empty_like(b)
+    ptr = lambda a: a.ctypes.data
+    gnn._lib.check(lib.gnnb_gcn_conv_step_host(g2.plan().h, ptr(x), ptr(W), ptr(b) if with_bias else None, relu_flag, D, D,
+                                               ptr(dy) if bwd else None, ptr(y), ptr(dx) if bwd else None,
+                                               ptr(dW) if bwd else None, ptr(db) if (bwd and with_bias) else None))
+    s2, t2 = oracle.add_self_loops(s, t, n)
+    p, c = oracle.gcn_propagate(s2, t2, n, x.astype(np.float64))
+    pre = p @ W.astype(np.float64).T + (b if with_bias else 0)
+    ref = np.maximum(pre, 0) if relu_flag else pre
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-5
+    # the device-side layer runs the same kernels: identical bits
+    layer = gnn.GCNConv(D, D, torch.relu if relu_flag else gnn.layers.identity, bias=with_bias, device="cuda")
+    with torch.no_grad():
+        layer.weight.copy_(torch.as_tensor(W))
+        if with_bias:
+            layer.bias.copy_(torch.as_tensor(b))
+    xt = gnn.unrows(torch.as_tensor(x).cuda()).requires_grad_(True)
+    yt = layer(g, xt)
+    assert np.array_equal(gnn.rows(yt.detach()).cpu().numpy(), y)
+    if bwd:
+        yt.backward(gnn.unrows(torch.as_tensor(dy).cuda()))
+        assert np.array_equal(gnn.rows(xt.grad).cpu().numpy(), dx)
+        assert np.array_equal(layer.weight.grad.cpu().numpy(), dW)
+        if with_bias:
+            assert np.array_equal(layer.bias.grad.cpu().numpy(), db)
