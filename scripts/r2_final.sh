@@ -19,3 +19,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -f -o gpurun_
 echo "ncu c4 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -f -o gpurun_out/prof_tc_r2 --kernel-name-base demangled -k regex:'linear_tf32x3|dw_tf32x3' -c 2 python scripts/profile_linear.py > gpurun_out/ncu_tc.log 2>&1
 echo "ncu tc rc=$?"
+# one ncu --set full pass over every kernel family (N = 2 M, E = 20 M), summarised into a table
+timeout 1200 ncu --set full --clock-control none -f -o gpurun_out/all_kernels_r2 --kernel-name-base demangled -k regex:'gnnb|tc::|tcw::' python scripts/run_all_kernels.py > gpurun_out/ncu_all.log 2>&1
+echo "ncu all kernels rc=$?"; tail -n 2 gpurun_out/ncu_all.log | cut -c1-200
