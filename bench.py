@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-nodes", type=int, default=None, help="bounded CPU sample: nodes")
     ap.add_argument("--cpu-edges", type=int, default=None, help="bounded CPU sample: edges")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg (debug)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size parity check of the partitioned path (debug)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (debug)")
     ap.add_argument("--ref-sample", action="store_true", help="--impl reference on the bounded sample instead of the full size")
     a = ap.parse_args()
@@ -193,6 +194,109 @@ def cpu_gcn_step_port(n, E, D, steps=1, keep=False):
             del A, p, pre
         del xs, dpre, dp, dxs
     return min(times), oracle, res
+
+
+def dist_parity(args, dg, layer, samples=320, max_deg=20000):
+    """Parity of the node-partitioned path at the run's FULL size (every rank calls this; it runs collectives).
+
+    Inputs are a pure function of the GLOBAL node id, so any rank can restate any row.  (1) A sample of this rank's rows
+    (the high-degree head of its deal and random ones; rows whose in+out degree exceeds `max_deg` are dropped so that the
+    CPU side stays small): their in- and out-edges are found by scanning the generated edge list again with torch ops,
+    the in-degrees by a histogram of the same scan, and the ORACLE (gather -> scatter with the reference's c .* (A (c .* x))
+    order, conv.jl:52-67) evaluates those rows of propagate, of the layer's forward and of the transposed propagate that
+    the backward pass runs.  (2) The adjoint identity <A z, r> = <z, A' r> over ALL rows of all ranks ties the two shards
+    (forward, transposed) of every rank together.  Normwise relative errors, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gnnb200 as gnn
+    from gnnb200 import partition
+    oracle = oracle_module()
+    n, E, D = args.nodes, args.edges, args.dim
+    dev, nl, rank = dg.device, dg.n_local, dg.rank
+    g_local = dg.local_nodes().long()
+
+    def feat(ids, salt):
+        j = torch.arange(D, device=ids.device, dtype=torch.int64)
+        v = (ids[:, None] * 1000003 + j[None, :] * 7919 + salt) % 65521
+        return (v.double() / 65521.0 - 0.5).float()
+
+    def fill(salt):
+        out = torch.empty(nl, D, device=dev)
+        for i in range(0, nl, 1 << 20):
+            out[i:i + (1 << 20)] = feat(g_local[i:i + (1 << 20)], salt)
+        return out
+
+    gen = torch.Generator(device="cpu").manual_seed(99 + rank)
+    idx = torch.unique(torch.cat([torch.arange(min(64, nl)), torch.randint(0, nl, (samples,), generator=gen)])).to(dev)
+    tg = g_local[idx]
+
+    c, cf, cb = dg.gcn_c()
+    z, r = fill(1), fill(2)
+    p = dg.propagate(dg.fwd, z, cf, c)
+    q = dg.propagate(dg.bwd, r, cb, c)
+    dots = torch.stack([(p * r).sum(dtype=torch.float64), (z * q).sum(dtype=torch.float64)])
+    dist.all_reduce(dots)
+    adjoint = abs(float(dots[0] - dots[1])) / max(abs(float(dots[0])), 1e-300)
+    p_s, q_s = p[idx].cpu().numpy(), q[idx].cpu().numpy()
+    del p, q, r
+    with torch.no_grad():
+        y = partition.dist_gcn_conv(layer, dg, gnn.unrows(z))
+    y_s = gnn.rows(y)[idx].cpu().numpy()
+    del y, z
+    torch.cuda.empty_cache()
+
+    # the sampled rows' edges and every node's in-degree, from the edge list itself
+    deg = torch.zeros(n, dtype=torch.int32, device=dev)
+    mark = torch.zeros(n, dtype=torch.bool, device=dev)
+    mark[tg] = True
+    ones = torch.ones(min(1 << 26, max(E, 1)), dtype=torch.int32, device=dev)
+    ks, kt = [], []
+    for s, t in partition.rmat_chunks(n, E, SEED, dev, 1 << 26):
+        deg.index_add_(0, t, ones[:t.numel()])
+        m = mark[s] | mark[t]
+        ks.append(s[m])
+        kt.append(t[m])
+    ks, kt = torch.cat(ks), torch.cat(kt)
+    del ones
+    tgs, perm = torch.sort(tg)
+    din = deg[tgs].long()
+    ms = mark[ks]
+    dout = torch.bincount(torch.searchsorted(tgs, ks[ms]), minlength=tgs.numel())
+    ok = (din + dout) <= max_deg
+    mark[tgs[~ok]] = False
+    V = tgs[ok]
+    rows_of_V = perm[ok].cpu().numpy()                       # positions in idx / p_s / y_s / q_s
+
+    def restate(src, dst, salt):
+        """rows V of c .* scatter(+, gather(c .* x, src), dst) on the graph with self loops, by the oracle"""
+        keep = mark[dst]
+        src, dst = torch.cat([src[keep], V]), torch.cat([dst[keep], V])          # + the self loops of V (conv.jl:26-27)
+        U = torch.unique(torch.cat([src, V]))
+        sc, dc = torch.searchsorted(U, src).cpu().numpy(), torch.searchsorted(U, dst).cpu().numpy()
+        cU = (1.0 / np.sqrt((deg[U] + 1).cpu().numpy().astype(np.float32))).astype(np.float32)   # in-degree incl. self loop
+        xs = feat(U, salt).cpu().numpy() * cU[:, None]
+        out = oracle.propagate_unfused("+", sc, dc, int(U.numel()), xs, None) * cU[:, None]
+        return out[torch.searchsorted(U, V).cpu().numpy()]
+
+    e_p = e_y = e_q = 0.0
+    if V.numel():
+        p_ref = restate(ks, kt, 1)
+        W = layer.weight.detach().cpu().numpy()
+        b = layer.bias.detach().cpu().numpy() if layer.bias is not None else 0.0
+        y_ref = np.maximum(p_ref @ W.T + b, 0)
+        q_ref = restate(kt, ks, 2)
+        e_p, e_y, e_q = relerr(p_s[rows_of_V], p_ref), relerr(y_s[rows_of_V], y_ref), relerr(q_s[rows_of_V], q_ref)
+    st = torch.tensor([e_p, e_y, e_q, float(V.numel()), float((~ok).sum()), float(din[ok].sum() + dout[ok].sum())],
+                      device=dev, dtype=torch.float64)
+    mx, sm = st.clone(), st.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(sm)
+    return {"propagate_rows": float(mx[0]), "layer_forward_rows": float(mx[1]), "transposed_propagate_rows": float(mx[2]),
+            "adjoint_identity_all_rows": adjoint, "rows_checked": int(sm[3]), "rows_dropped_for_degree": int(sm[4]),
+            "edges_restated": int(sm[5]),
+            "method": "full-size graph; oracle restatement (gather/scatter, conv.jl:52-67 order) of sampled rows of every "
+                      "rank from the regenerated edge list + <Az,r> = <z,A'r> over all rows; normwise, max over ranks"}
 
 
 def cpu_leg_gcn(args, gpu_replay=None):
@@ -819,7 +923,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.backends.cuda.matmul.allow_tf32 = False   # fp32 GEMM like the reference (cuBLAS sgemm)
     torch.backends.cudnn.allow_tf32 = False
-    if world > 1:
+    if world > 1 or os.environ.get("GNNB_BENCH_PARTITIONED"):   # the env switch: the partitioned path on one rank (debug)
         dist.init_process_group("nccl", device_id=dev)
         if args.config not in (2, 5):
             raise SystemExit("configs 1, 3, 4 are single-GPU workloads")
@@ -827,7 +931,8 @@ def run_ours(args):
         if args.config == 5 and "GNNB_HALO_BUFFERS" not in os.environ:
             os.environ["GNNB_HALO_BUFFERS"] = "1"    # 1 KB rows: one halo buffer per shard (forward and backward alternate)
         return partition.bench_multi(args, world, int(os.environ.get("RANK", "0")), dev, SEED, ClockSampler, measured_peaks,
-                                     cpu_leg=None if args.no_cpu else (lambda: cpu_leg_gcn(args)[0]))
+                                     cpu_leg=None if args.no_cpu else (lambda: cpu_leg_gcn(args)[0]),
+                                     parity=None if args.no_parity else (lambda dg, layer: dist_parity(args, dg, layer)))
     if args.config == 5:
         raise SystemExit("config 5 (1 B edges, 256-wide rows) needs the 8 GPUs of a box: launch with torchrun --nproc-per-node 8")
     fn = {1: run_config1, 2: run_config2, 3: run_config3, 4: run_config4}[args.config]

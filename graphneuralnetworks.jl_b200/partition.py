@@ -138,6 +138,19 @@ class _Shard:
         self.push = None           # per-D state of the peer-to-peer push path (_PushState)
 
 
+def rmat_chunks(num_nodes: int, num_edges: int, seed: int, device, chunk_edges: int = 1 << 26):
+    """the counter-based RMAT list of gnnb_rmat_edges as (src, dst) int64 chunks generated on `device`; the two buffers are
+    reused, so a chunk is valid until the next one is requested"""
+    dev = torch.device(device)
+    cap = min(chunk_edges, max(num_edges, 1))
+    s, t = (torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(2))
+    for first in range(0, num_edges, chunk_edges):
+        cnt = min(chunk_edges, num_edges - first)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gnnb_rmat_edges_range(num_nodes, first, cnt, seed, s.data_ptr(), t.data_ptr(), _stream(dev)))
+        yield s[:cnt], t[:cnt]
+
+
 class DistGraph:
     """A GNNGraph partitioned over the ranks of `group`.
 
@@ -222,18 +235,7 @@ class DistGraph:
     def from_rmat(cls, num_nodes: int, num_edges: int, seed: int = 17, *, device, chunk_edges: int = 1 << 26, **kw):
         """the RMAT list of gnnb_rmat_edges, generated (identically on every rank) and consumed chunk by chunk"""
         dev = torch.device(device)
-
-        buf = [torch.empty(min(chunk_edges, max(num_edges, 1)), dtype=torch.int64, device=dev) for _ in range(2)]
-
-        def gen():
-            s, t = buf
-            for first in range(0, num_edges, chunk_edges):
-                cnt = min(chunk_edges, num_edges - first)
-                with torch.cuda.device(dev):
-                    _lib.check(lib.gnnb_rmat_edges_range(num_nodes, first, cnt, seed, s.data_ptr(), t.data_ptr(), _stream(dev)))
-                yield s[:cnt], t[:cnt]
-
-        return cls(None, None, num_nodes, chunks=gen, device=dev, **kw)
+        return cls(None, None, num_nodes, chunks=lambda: rmat_chunks(num_nodes, num_edges, seed, dev, chunk_edges), device=dev, **kw)
 
     def local_nodes(self) -> torch.Tensor:
         """0-based global node id of every local row, in local-row order"""
@@ -500,7 +502,7 @@ def dist_gcn_conv(l, dg: DistGraph, x_local: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------
 # bench.py --gpus N>1
 # ---------------------------------------------------------------------------------------------------------
-def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_leg=None):
+def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_leg=None, parity=None):
     import gnnb200 as gnn
     n, E, D = args.nodes, args.edges, args.dim
     torch.cuda.synchronize()
@@ -642,6 +644,12 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_
                "h2d_bytes_per_step": 2 * 4 * n * D, "d2h_bytes_per_step": 2 * 4 * n * D + 4 * D * D * world,
                "api": "gnnb200.partition.dist_gcn_conv on pinned host slices (all ranks; bytes are whole-job)"}
 
+    par = None
+    if parity is not None:                                   # all ranks: the checker runs collectives
+        del x, dy, xr, out
+        layer.weight.grad = None
+        torch.cuda.empty_cache()
+        par = parity(dg, layer)
     cpu = None
     if rank == 0 and cpu_leg is not None:
         cpu = cpu_leg()                                      # the oracle port on the bounded sample, host cores of rank 0
@@ -663,13 +671,13 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": float(allst[worst, 6]), "peak": peak, "unit": "GB/s",
                          "frac": float(allst[worst, 6]) / peak, "traffic": None,
-                         "kernel": "gnnb::seg_reduce_kernel<4,32,1,false> over [local|halo] rows (slowest rank)",
+                         "kernel": "gnnb::seg_lean_kernel (sum, per-edge scale stream, halo base) over [local|halo] rows (slowest rank)",
                          "peak_source": peak_src,
                          "halo": {"bytes_received_slowest_rank": float(allst[:, 4].max()) * D * 4,
                                   "ms": float(allst[:, 1].max()),
                                   "GBps_per_gpu": float(allst[:, 4].max()) * D * 4 / (float(allst[:, 1].max()) * 1e-3) / 1e9,
                                   "nvlink_peak_GBps": 770.0}},
-            "cpu_baseline": cpu, "parity_rel_err": None,
+            "cpu_baseline": cpu, "parity_rel_err": par,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
