@@ -89,6 +89,8 @@ _SIGS = {
     "gnnb_gat_aggregate_bwd": (_int, [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, C.c_float,
                                       _f32p, _f32p, _f32p, _vp]),
     "gnnb_linear": (_int, [_f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _f32p, _vp]),
+    "gnnb_bias_act": (_int, [_f32p, _f32p, _int, _i64, _i64, _f32p, _vp]),
+    "gnnb_bias_act_bwd": (_int, [_f32p, _f32p, _int, _i64, _i64, _f32p, _f32p, _vp]),
     "gnnb_linear_bwd": (_int, [_f32p, _f32p, _f32p, _f32p, _int, _i64, _i64, _i64, _f32p, _f32p, _f32p, _f32p, _vp]),
     "gnnb_dense_set_emulation": (_int, [_int]),
     "gnnb_dense_set_tensor_core_kernel": (_int, [_int]),

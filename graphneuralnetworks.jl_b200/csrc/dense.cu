@@ -132,6 +132,22 @@ __global__ void place_block_kernel(const float* __restrict__ blk, int rows, int 
     if (i < rows * cols) { const int r = i / cols, c = i % cols; out[(size_t)r * ld + c] = blk[i]; }
 }
 
+// y = act(x + bias): the layers' closing `σ.(x .+ bias)` when no GEMM epilogue can carry it (GATConv, conv.jl:149)
+template <int RELU>
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bias, int64_t nvec,
+                                                       int nv, float* __restrict__ y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % nv));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+}
+
 // dpre = dy * (y > 0) (relu pullback, y = forward output) or dpre = dy; partial column sums per block for db
 template <int RELU>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
@@ -261,6 +277,52 @@ int gnnb_linear2_bwd(const float* dy, const float* y, const float* x1, const flo
     return GNNB_OK;
 }
 
+// the relu mask x upstream gradient and the deterministic two-stage bias gradient, one pass over dy (and y)
+static int act_bwd_launch(const float* dy, const float* y, int relu, int64_t N, int64_t D, float* dpre, float* db, cudaStream_t st) {
+    // about 8 CTAs per SM worth of blocks: long row runs per block keep the deterministic final pass short
+    int64_t rpb = ceil_div(N, 148 * 8);
+    const int rows_per_block = (int)(rpb < 64 ? 64 : rpb);
+    const int nblocks = (int)ceil_div(N, rows_per_block);
+    float* partial = nullptr;
+    if (db) {
+        static float* part_buf = nullptr; static size_t part_bytes = 0;
+        const size_t need = sizeof(float) * (size_t)nblocks * D;
+        if (part_bytes < need) { if (part_buf) { cudaDeviceSynchronize(); cudaFree(part_buf); } GNNB_CUDA(cudaMalloc(&part_buf, need)); part_bytes = need; }
+        partial = part_buf;
+    }
+    if (relu) act_bwd_kernel<1><<<nblocks, 256, 0, st>>>(dy, y, N, (int)D, dpre, partial, rows_per_block);
+    else act_bwd_kernel<0><<<nblocks, 256, 0, st>>>(dy, y, N, (int)D, nullptr, partial, rows_per_block);
+    GNNB_LAUNCHED();
+    if (db) { colsum_final_kernel<<<(unsigned)ceil_div(D, 128), 128, 0, st>>>(partial, nblocks, (int)D, db); GNNB_LAUNCHED(); }
+    return GNNB_OK;
+}
+
+int gnnb_bias_act(const float* x, const float* bias, int relu, int64_t N, int64_t D, float* y, void* stream) {
+    if (N < 0 || D <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
+    if (N == 0) return GNNB_OK;
+    if (!x || !y) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
+    if (D % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)y & 15) || (bias && ((uintptr_t)bias & 15)))
+        GNNB_FAIL(GNNB_EUNSUPPORTED, "bias_act: D must be a multiple of 4 and pointers 16 B aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nvec = N * (D / 4);
+    const unsigned grid = (unsigned)(ceil_div(nvec, 256) < 148 * 16 ? ceil_div(nvec, 256) : 148 * 16);
+    if (relu) bias_act_kernel<1><<<grid, 256, 0, st>>>(x, bias, nvec, (int)(D / 4), y);
+    else bias_act_kernel<0><<<grid, 256, 0, st>>>(x, bias, nvec, (int)(D / 4), y);
+    GNNB_LAUNCHED();
+    return GNNB_OK;
+}
+
+int gnnb_bias_act_bwd(const float* dy, const float* y, int relu, int64_t N, int64_t D, float* dpre, float* db, void* stream) {
+    if (N < 0 || D <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0) { if (db) GNNB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)D, st)); return GNNB_OK; }
+    if (!dy || (relu && (!y || !dpre))) GNNB_FAIL(GNNB_EINVAL, "NULL argument");
+    if (!relu && !db) return GNNB_OK;
+    if (D % 4 != 0 || D > 1024 || ((uintptr_t)dy & 15) || (relu && (((uintptr_t)y & 15) || ((uintptr_t)dpre & 15))))
+        GNNB_FAIL(GNNB_EUNSUPPORTED, "bias_act_bwd: D must be a multiple of 4 (<= 1024) and pointers 16 B aligned");
+    return act_bwd_launch(dy, y, relu, N, D, dpre, db, st);
+}
+
 int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float* W, int relu, int64_t N, int64_t Din,
                     int64_t Dout, float* dpre_ws, float* dx, float* dW, float* db, void* stream) {
     if (N < 0 || Din <= 0 || Dout <= 0) GNNB_FAIL(GNNB_ESIZE, "bad sizes");
@@ -276,21 +338,7 @@ int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float
     if ((relu || db) && N > 0) {
         if (Dout % 4 != 0 || Dout > 1024 || ((uintptr_t)dy & 15) || (relu && (((uintptr_t)y & 15) || ((uintptr_t)dpre_ws & 15))))
             GNNB_FAIL(GNNB_EUNSUPPORTED, "linear_bwd: Dout must be a multiple of 4 (<= 1024) and pointers 16 B aligned");
-        // about 8 CTAs per SM worth of blocks: long row runs per block keep the deterministic final pass short
-        int64_t rpb = ceil_div(N, 148 * 8);
-        const int rows_per_block = (int)(rpb < 64 ? 64 : rpb);
-        const int nblocks = (int)ceil_div(N, rows_per_block);
-        float* partial = nullptr;
-        if (db) {
-            static float* part_buf = nullptr; static size_t part_bytes = 0;
-            const size_t need = sizeof(float) * (size_t)nblocks * Dout;
-            if (part_bytes < need) { if (part_buf) { cudaDeviceSynchronize(); cudaFree(part_buf); } GNNB_CUDA(cudaMalloc(&part_buf, need)); part_bytes = need; }
-            partial = part_buf;
-        }
-        if (relu) act_bwd_kernel<1><<<nblocks, 256, 0, st>>>(dy, y, N, (int)Dout, dpre_ws, partial, rows_per_block);
-        else act_bwd_kernel<0><<<nblocks, 256, 0, st>>>(dy, y, N, (int)Dout, nullptr, partial, rows_per_block);
-        GNNB_LAUNCHED();
-        if (db) { colsum_final_kernel<<<(unsigned)ceil_div(Dout, 128), 128, 0, st>>>(partial, nblocks, (int)Dout, db); GNNB_LAUNCHED(); }
+        GNNB_TRY(act_bwd_launch(dy, y, relu, N, Dout, dpre_ws, db, st));
         if (relu) dpre = dpre_ws;
     } else if (db && N == 0) {
         GNNB_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * Dout, st));

@@ -495,8 +495,8 @@ def dist_gcn_conv(l, dg: DistGraph, x_local: torch.Tensor) -> torch.Tensor:
     pr = unrows(_DistGCNPropagateFn.apply(rows(x), dg))
     if Dout >= Din:
         return _linear(l, W, pr, True)            # σ.(W * x .+ b): GEMM with the bias/relu epilogue
-    from .layers import _add_bias, _bias, _sigma
-    return _sigma(l)(_add_bias(pr, _bias(l)))
+    from .layers import _bias_act
+    return _bias_act(l, pr)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -221,6 +221,12 @@ int gnnb_linear2(const float* x1, const float* x2, const float* W, const float* 
 int gnnb_linear2_bwd(const float* dy, const float* y, const float* x1, const float* x2, const float* W, int relu, int64_t N,
                      int64_t Din1, int64_t Din2, int64_t Dout, float* dpre_ws, float* dx1, float* dx2, float* dW, float* db,
                      void* stream);
+/* y = act(x .+ bias) on (D,N) features and its pullback, for layers whose closing `σ.(x .+ bias)` follows an aggregation
+ * rather than a GEMM (GATConv: GNNlib/src/layers/conv.jl:149): one pass each instead of the broadcast-add, the
+ * activation, the mask product and the column reduction.  bias NULL or D floats; relu 0/1; y may alias x.
+ * bwd: dpre = dy .* (y > 0) (relu only; dpre may alias dy), db = sum over nodes of dpre (NULL to skip; deterministic). */
+int gnnb_bias_act(const float* x, const float* bias, int relu, int64_t N, int64_t D, float* y, void* stream);
+int gnnb_bias_act_bwd(const float* dy, const float* y, int relu, int64_t N, int64_t D, float* dpre, float* db, void* stream);
 /* 1 (default) = try the fp32-emulated tensor-core GEMM; 0 = force the SIMT sgemm.  *_active: -1 not yet used,
  * 0 unavailable / off, 1 in use. */
 int gnnb_dense_set_emulation(int on);

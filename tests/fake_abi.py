@@ -327,6 +327,24 @@ class FakeLib:
         _arr(der, (p.ns, H))[...] = _segment(SUM, dz, p.s, p.ns)
         return OK
 
+    def gnnb_bias_act(self, x, bias, relu, N, D, y, stream):
+        self.calls.append("gnnb_bias_act")
+        pre = _arr(x, (N, D)).astype(np.float64)
+        if bias is not None:
+            pre = pre + _arr(bias, (D,)).astype(np.float64)
+        _arr(y, (N, D))[...] = np.maximum(pre, 0) if relu else pre
+        return OK
+
+    def gnnb_bias_act_bwd(self, dy, y, relu, N, D, dpre, db, stream):
+        self.calls.append("gnnb_bias_act_bwd")
+        d = _arr(dy, (N, D)).astype(np.float64)
+        if relu:
+            d = d * (_arr(y, (N, D)) > 0)
+            _arr(dpre, (N, D))[...] = d
+        if db is not None:
+            _arr(db, (D,))[...] = d.sum(0)
+        return OK
+
     def gnnb_linear2(self, x1, x2, W, bias, relu, N, Din1, Din2, Dout, y, stream):
         self.calls.append("gnnb_linear2")
         Wm = _arr(W, (Dout, Din1 + Din2)).astype(np.float64)

@@ -1013,3 +1013,62 @@ def test_linear2_c_abi(gnn, N, D1, D2, relu_flag, with_bias):
     if with_bias:
         assert rel(db.cpu(), dpre.sum(0).cpu()) < 5e-6
     assert lib.gnnb_dense_tc_error() == 0
+
+
+@pytest.mark.parametrize("N,D", [(70001, 512), (1, 4), (4099, 36), (0, 64)])
+@pytest.mark.parametrize("relu_flag,with_bias", [(1, True), (0, True), (1, False)])
+def test_bias_act_c_abi(gnn, N, D, relu_flag, with_bias):
+    """gnnb_bias_act / gnnb_bias_act_bwd — σ.(x .+ b), the closing line of GATConv (conv.jl:149): exact forward (one add, one
+    max), exact mask product, deterministic bias gradient against float64."""
+    lib = gnn._lib.lib
+    gen = torch.Generator(device="cuda").manual_seed(N + D)
+    x = torch.randn(N, D, device="cuda", generator=gen)
+    b = torch.randn(D, device="cuda", generator=gen) if with_bias else None
+    dy = torch.randn(N, D, device="cuda", generator=gen)
+    y = torch.full((N, D), float("nan"), device="cuda")
+    gnn._lib.check(lib.gnnb_bias_act(x.data_ptr() if N else None, None if b is None else b.data_ptr(), relu_flag, N, D,
+                                     y.data_ptr() if N else None, None))
+    pre = x if b is None else x + b
+    assert torch.equal(y, pre.clamp(min=0) if relu_flag else pre)
+    dpre = torch.full((N, D), float("nan"), device="cuda")
+    dbs = []
+    for _ in range(2):
+        db = torch.full((D,), float("nan"), device="cuda")
+        gnn._lib.check(lib.gnnb_bias_act_bwd(dy.data_ptr() if N else None, y.data_ptr() if N else None, relu_flag, N, D,
+                                             dpre.data_ptr() if (N and relu_flag) else None, db.data_ptr() if with_bias else None, None))
+        dbs.append(db)
+    ref = dy * (y > 0) if relu_flag else dy
+    if relu_flag:
+        assert torch.equal(dpre, ref)
+    if with_bias:
+        assert torch.equal(dbs[0], dbs[1])
+        if N:
+            assert rel(dbs[0].cpu(), ref.double().sum(0).cpu()) < 2e-6
+        else:
+            assert float(dbs[0].abs().max()) == 0.0
+
+
+def test_gat_conv_closing_line_uses_the_fused_pass(gnn, small_graph):
+    """GATConv's σ.(x .+ bias) goes through gnnb_bias_act (one kernel) and differentiates like the torch composition"""
+    _, _, _, n, g = small_graph
+    torch.manual_seed(3)
+    l = gnn.GATConv(32, 16, torch.relu, heads=4, device="cuda")
+    with torch.no_grad():
+        l.bias.normal_()
+    x = torch.randn(32, n, device="cuda", requires_grad=True)
+    n0 = gnn.launch_count()
+    y = gnn.gat_conv(l, g, x)
+    assert gnn.launch_count() > n0
+    dy = torch.randn_like(y)
+    gx, ga, gb, gw = torch.autograd.grad(y, [x, l.a, l.bias, l.dense_x.weight], dy)
+    from gnnb200 import layers as L
+    saved = L._bias_act
+    try:
+        L._bias_act = lambda ll, out: L._sigma(ll)(L._add_bias(out, L._bias(ll)))
+        y2 = gnn.gat_conv(l, g, x)
+        gx2, ga2, gb2, gw2 = torch.autograd.grad(y2, [x, l.a, l.bias, l.dense_x.weight], dy)
+    finally:
+        L._bias_act = saved
+    assert torch.equal(y, y2)
+    for a_, b_ in ((gx, gx2), (ga, ga2), (gw, gw2), (gb, gb2)):
+        assert rel(a_.cpu(), b_.cpu()) < 2e-6
