@@ -352,6 +352,20 @@ int gnnb_linear_bwd(const float* dy, const float* y, const float* x, const float
         const int rc = linear_tf32x3(dpre, wt, nullptr, 0, N, Dout, Din, dx, st);
         if (rc == GNNB_OK) dx = nullptr;
         else if (rc != GNNB_EUNSUPPORTED) return rc;
+    } else if (dx && g_tc_enabled && (Dout > 128 || Din > 128) && Dout % 32 == 0 && Dout <= 2048 && Din % 128 == 0 && Din <= 1024 &&
+               N >= 2048) {
+        // wide shapes: the same product through the wide tcgen05 kernel on a transposed copy of W (<= 8 MB, kept)
+        static float* wtw = nullptr; static size_t wtw_elems = 0;
+        if (wtw_elems < (size_t)(Dout * Din)) {
+            if (wtw) { cudaDeviceSynchronize(); cudaFree(wtw); wtw = nullptr; wtw_elems = 0; }
+            GNNB_CUDA(cudaMalloc(&wtw, sizeof(float) * (size_t)(Dout * Din)));
+            wtw_elems = (size_t)(Dout * Din);
+        }
+        transpose_small_kernel<<<(unsigned)ceil_div(Dout * Din, 256), 256, 0, st>>>(W, (int)Dout, (int)Din, wtw);
+        GNNB_LAUNCHED();
+        const int rc = linear_tf32x3(dpre, wtw, nullptr, 0, N, Dout, Din, dx, st);
+        if (rc == GNNB_OK) dx = nullptr;
+        else if (rc != GNNB_EUNSUPPORTED) return rc;
     }
     // dX(Din x N) = W^T-as-stored(Din x Dout) dPre(Dout x N)
     if (dx) GNNB_TRY(lt::matmul(CUBLAS_OP_N, CUBLAS_OP_N, Din, N, Dout, W, Din, dpre, Dout, dx, Din, nullptr, 0, st));

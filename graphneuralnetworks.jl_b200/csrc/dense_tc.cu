@@ -458,6 +458,187 @@ __global__ void dw_reduce_kernel(const float* __restrict__ partial, int nparts, 
 }
 }  // namespace tcw
 
+// =====================================================================================================================
+// Wide shapes (K and/or Nout above 128: GATConv's 512 -> 8 x 64 projection, config 5's 256 -> 256 layer).  W no longer
+// fits beside the ring, so every stage carries one K-block of BOTH operands: 128 rows of X and 128 rows of W (one column
+// quarter of the output), each split big/small by the loaders.  Item order per CTA: row tile -> output quarter -> K-block;
+// the X tile is re-read from L2 for every quarter (HBM sees it once), W (<= 1 MB) lives in L2.
+// The big*big products accumulate in one TMEM accumulator and the two cross terms in a second one: the tensor core's
+// accumulator truncates (dw_tf32x3 below measured ~2^-25.7 of the running sum per accumulation), so the chain that carries
+// the full-magnitude sum is kept at K/8 accumulations (64 at K = 512) while the 2K/8 cross-term accumulations act on a sum
+// 2^-11 smaller.  The epilogue adds the two.  Two such pairs (4 x 128 columns = all of TMEM) double-buffer MMA and epilogue.
+// =====================================================================================================================
+namespace tcx {
+using namespace tc;
+constexpr int XSTAGE = 3;
+constexpr int XSTAGE_BYTES = 4 * KBLK_BYTES;                    // X big, X small, W big, W small: 64 KB
+constexpr int SMEM_EPI_X = XSTAGE * XSTAGE_BYTES;
+constexpr int SMEM_BIAS_X = SMEM_EPI_X + 4 * 32 * EPI_LD * 4;
+constexpr int MAX_NOUT = 1024;
+constexpr int SMEM_BAR_X = SMEM_BIAS_X + MAX_NOUT * 4;
+constexpr int SMEM_TOTAL_X = SMEM_BAR_X + 128;
+
+__global__ void __launch_bounds__(THREADS, 1) linear_wide_tf32x3_kernel(const Params p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KB = p.K / BK;                                   // K-blocks per (tile, quarter)
+    const int NQ = p.Nout / 128;                               // output quarters of 128 columns
+    const int64_t ntiles = (p.M + BM - 1) / BM;
+    const int64_t my_tiles = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t sbase = s_u32(smem);
+    const uint32_t bar_full = sbase + SMEM_BAR_X;              // [XSTAGE]
+    const uint32_t bar_empty = bar_full + 8 * XSTAGE;          // [XSTAGE]
+    const uint32_t bar_tfull = bar_empty + 8 * XSTAGE;         // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR_X + 8 * (2 * XSTAGE + 4));
+    float* sbias = reinterpret_cast<float*>(smem + SMEM_BIAS_X);
+
+    if (tid == 0) {
+        for (int s = 0; s < XSTAGE; ++s) { bar_init(bar_full + 8 * s, LOADERS); bar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8 * a, 1); bar_init(bar_tempty + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < p.Nout; i += THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ================= loaders: 4 + 4 float4 per thread and stage, the next stage's already in flight =================
+        const int c = tid & 7, r32 = tid >> 3, rr = r32 & 7;
+        const int per_tile = NQ * KB;
+        const int64_t total = my_tiles * per_tile;
+        auto fetch = [&](int64_t item, float4* va, float4* vw) {
+            const int64_t tile = blockIdx.x + (item / per_tile) * gridDim.x;
+            const int rem = (int)(item % per_tile);
+            const int nq = rem / KB, kb = rem - nq * KB;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t row = tile * BM + r32 + 32 * i;
+                va[i] = (item < total && row < p.M)
+                            ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.K + kb * BK) + c)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int n = nq * 128 + r32 + 32 * i;
+                vw[i] = (item < total) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.ldw + kb * BK) + c)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 va[4], vw[4], na[4], nw[4];
+        fetch(0, va, vw);
+        for (int64_t it = 0; it < total; ++it) {
+            fetch(it + 1, na, nw);
+            const int stage = (int)(it % XSTAGE);
+            if (!bar_wait(bar_empty + 8 * stage, (uint32_t)(((it / XSTAGE) & 1) ^ 1), p.err)) break;
+            unsigned char* sa = smem + stage * XSTAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int off = ((r32 >> 3) + 4 * i) * 1024 + rr * 128 + ((c ^ rr) << 4);
+                float4 b = make_float4(tf32_big(va[i].x), tf32_big(va[i].y), tf32_big(va[i].z), tf32_big(va[i].w));
+                *reinterpret_cast<float4*>(sa + off) = b;
+                *reinterpret_cast<float4*>(sa + KBLK_BYTES + off) = make_float4(va[i].x - b.x, va[i].y - b.y, va[i].z - b.z, va[i].w - b.w);
+                b = make_float4(tf32_big(vw[i].x), tf32_big(vw[i].y), tf32_big(vw[i].z), tf32_big(vw[i].w));
+                *reinterpret_cast<float4*>(sa + 2 * KBLK_BYTES + off) = b;
+                *reinterpret_cast<float4*>(sa + 3 * KBLK_BYTES + off) = make_float4(vw[i].x - b.x, vw[i].y - b.y, vw[i].z - b.z, vw[i].w - b.w);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bar_arrive(bar_full + 8 * stage);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { va[i] = na[i]; vw[i] = nw[i]; }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================= MMA issuer: M = 128, N = 128 per instruction =================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        uint32_t it = 0, ucount = 0;                           // ucount: (tile, quarter) units done by this CTA
+        bool alive = true;
+        const int64_t units = my_tiles * NQ;
+        for (int64_t u = 0; alive && u < units; ++u, ++ucount) {
+            const int acc = ucount & 1;
+            if (!bar_wait(bar_tempty + 8 * acc, ((ucount >> 1) & 1) ^ 1, p.err)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_main = tmem_base + acc * 256, d_cross = d_main + 128;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int stage = it % XSTAGE;
+                if (!bar_wait(bar_full + 8 * stage, (it / XSTAGE) & 1, p.err)) { alive = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t a_big = sbase + stage * XSTAGE_BYTES, a_small = a_big + KBLK_BYTES;
+                    const uint32_t w_big = a_big + 2 * KBLK_BYTES, w_small = a_big + 3 * KBLK_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t o = j * 32;
+                        umma_tf32(d_cross, umma_desc(a_small + o), umma_desc(w_big + o), idesc, (kb | j) != 0);
+                        umma_tf32(d_cross, umma_desc(a_big + o), umma_desc(w_small + o), idesc, 1u);
+                        umma_tf32(d_main, umma_desc(a_big + o), umma_desc(w_big + o), idesc, (kb | j) != 0);
+                    }
+                    umma_commit(bar_empty + 8 * stage);
+                    if (kb == KB - 1) umma_commit(bar_tfull + 8 * acc);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue: main + cross + bias (+ addend), activation, whole 128 B row segments =================
+        const int q = warp & 3;
+        uint32_t ucount = 0;
+        float* stg = reinterpret_cast<float*>(smem + SMEM_EPI_X) + q * (32 * EPI_LD);
+        for (int64_t t = 0; t < my_tiles; ++t) {
+            const int64_t tile = blockIdx.x + t * gridDim.x;
+            const int64_t row0 = tile * BM + q * 32;
+            for (int nq = 0; nq < NQ; ++nq, ++ucount) {
+                const int acc = ucount & 1;
+                if (!bar_wait(bar_tfull + 8 * acc, (ucount >> 1) & 1, p.err)) goto done;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t r[32], r2[32];
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c0;
+                    tmem_ld32(ta, r);
+                    tmem_ld32(ta + 128, r2);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int cg = nq * 128 + c0;                  // first output column of this chunk
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) + sbias[cg + j];
+                        o.y = (__uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1])) + sbias[cg + j + 1];
+                        o.z = (__uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2])) + sbias[cg + j + 2];
+                        o.w = (__uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3])) + sbias[cg + j + 3];
+                        *reinterpret_cast<float4*>(stg + lane * EPI_LD + j) = o;
+                    }
+                    __syncwarp();
+                    const int f = (lane & 7) * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = (lane >> 3) + 4 * i;
+                        float4 o = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + f);
+                        if (row0 + rr < p.M) {
+                            const size_t at = (size_t)(row0 + rr) * p.Nout + cg + f;
+                            if (p.addend) {
+                                const float4 a = *reinterpret_cast<const float4*>(p.addend + at);
+                                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                            }
+                            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            *reinterpret_cast<float4*>(p.y + at) = o;
+                        }
+                    }
+                    __syncwarp();
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                bar_arrive(bar_tempty + 8 * acc);
+            }
+        }
+    done:;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+}  // namespace tcx
+
 static int* g_tc_err = nullptr;
 int g_tc_enabled = 1;
 
@@ -472,13 +653,20 @@ int linear_tf32x3(const float* x, const float* W, const float* bias, int relu, i
 int linear_tf32x3_ex(const float* x, const float* W, int64_t ldw, const float* bias, const float* addend, int relu, int64_t M,
                      int64_t K, int64_t Nout, float* y, cudaStream_t st) {
     if (!g_tc_enabled) return GNNB_EUNSUPPORTED;
-    if (K % 32 != 0 || K > 128 || Nout % 16 != 0 || Nout > 128 || Nout < 16 || ldw % 4 != 0 || ldw < K) return GNNB_EUNSUPPORTED;
+    const bool wide = K > 128 || Nout > 128;
+    if (wide) {
+        // (a handful of row tiles cannot fill the machine: the library GEMM takes those)
+        if (K % 32 != 0 || K > 2048 || Nout % 128 != 0 || Nout > tcx::MAX_NOUT || ldw % 4 != 0 || ldw < K || M < 2048) return GNNB_EUNSUPPORTED;
+    } else if (K % 32 != 0 || Nout % 16 != 0 || Nout < 16 || ldw % 4 != 0 || ldw < K) {
+        return GNNB_EUNSUPPORTED;
+    }
     if (((uintptr_t)x & 15) || ((uintptr_t)W & 15) || ((uintptr_t)y & 15) || ((uintptr_t)addend & 15)) return GNNB_EUNSUPPORTED;
     if (M == 0) return GNNB_OK;
     static bool configured = false;
     static int nsm = 0;
     if (!configured) {
         GNNB_CUDA(cudaFuncSetAttribute(tc::linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+        GNNB_CUDA(cudaFuncSetAttribute(tcx::linear_wide_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcx::SMEM_TOTAL_X));
         int dev = 0;
         GNNB_CUDA(cudaGetDevice(&dev));
         GNNB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -491,7 +679,8 @@ int linear_tf32x3_ex(const float* x, const float* W, int64_t ldw, const float* b
     p.ldw = (int)ldw; p.err = g_tc_err;
     const int64_t ntiles = ceil_div(M, tc::BM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
-    tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(p);
+    if (wide) tcx::linear_wide_tf32x3_kernel<<<grid, tc::THREADS, tcx::SMEM_TOTAL_X, st>>>(p);
+    else tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(p);
     GNNB_LAUNCHED();
     return GNNB_OK;
 }

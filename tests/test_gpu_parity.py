@@ -776,7 +776,10 @@ def test_halo_addressing_and_gather_rows(graph, oracle, gnn, variant, D):
 # --------------------------------------------------------------------------------------------- dense layer part
 @pytest.mark.parametrize("N,Din,Dout", [(1000, 128, 128), (777, 16, 8), (5000, 64, 256), (33, 1432, 16), (0, 8, 8),
                                         (4096, 64, 128), (130000, 128, 64), (300, 32, 16), (129, 96, 48), (1, 128, 128),
-                                        (400000, 128, 128), (70001, 96, 128)])
+                                        (400000, 128, 128), (70001, 96, 128),
+                                        # the wide tcgen05 kernel (K or Nout above 128, N >= 2048): GATConv 512 -> 8 x 64, config 5
+                                        (40000, 512, 512), (3000, 256, 256), (20001, 512, 128), (2048, 160, 384),
+                                        (9000, 1024, 1024)])
 @pytest.mark.parametrize("relu_flag,with_bias", [(1, True), (0, True), (1, False), (0, False)])
 @pytest.mark.parametrize("emulate", [1, 0])
 def test_linear_c_abi(gnn, N, Din, Dout, relu_flag, with_bias, emulate):
@@ -815,6 +818,24 @@ def test_linear_c_abi(gnn, N, Din, Dout, relu_flag, with_bias, emulate):
     finally:
         lib.gnnb_dense_set_emulation(1)
         lib.gnnb_dense_set_tensor_core_kernel(1)
+
+
+def test_linear_wide_accumulation_drift(gnn):
+    """All-positive operands at K = 512: every product has the same sign, the case in which the tensor core's truncating
+    accumulator drifts most.  The wide kernel keeps the full-magnitude chain at K/8 accumulations; the bar stays 5e-6."""
+    lib = gnn._lib.lib
+    N, K, Nout = 30000, 512, 512
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(N, K, device="cuda", generator=gen) + 0.5
+    W = torch.rand(Nout, K, device="cuda", generator=gen) + 0.5
+    y = torch.empty(N, Nout, device="cuda")
+    n0 = gnn.launch_count()
+    gnn._lib.check(lib.gnnb_linear(x.data_ptr(), W.data_ptr(), None, 0, N, K, Nout, y.data_ptr(), None))
+    assert gnn.launch_count() == n0 + 1                      # the hand-written kernel, not the library GEMM
+    ref = x.double() @ W.double().t()
+    assert rel(y.cpu(), ref.cpu()) < 5e-6
+    assert float(((y.double() - ref) / ref).abs().max()) < 2e-5
+    assert lib.gnnb_dense_tc_error() == 0
 
 
 # ---------------------------------------------------------------------------------- full-size properties (config 2)
