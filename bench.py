@@ -276,7 +276,7 @@ def dist_parity(args, dg, layer, samples=320, max_deg=20000):
         sc, dc = torch.searchsorted(U, src).cpu().numpy(), torch.searchsorted(U, dst).cpu().numpy()
         cU = (1.0 / np.sqrt((deg[U] + 1).cpu().numpy().astype(np.float32))).astype(np.float32)   # in-degree incl. self loop
         xs = feat(U, salt).cpu().numpy() * cU[:, None]
-        out = oracle.propagate_unfused("+", sc, dc, int(U.numel()), xs, None) * cU[:, None]
+        out = oracle.propagate_unfused("+", sc + 1, dc + 1, int(U.numel()), xs, None) * cU[:, None]   # the oracle is 1-based, like Julia
         return out[torch.searchsorted(U, V).cpu().numpy()]
 
     e_p = e_y = e_q = 0.0

@@ -511,22 +511,22 @@ __global__ void __launch_bounds__(THREADS, 1) linear_wide_tf32x3_kernel(const Pa
     if (warp < 8) {
         // ================= loaders: 4 + 4 float4 per thread and stage, the next stage's already in flight =================
         const int c = tid & 7, r32 = tid >> 3, rr = r32 & 7;
-        const int per_tile = NQ * KB;
-        const int64_t total = my_tiles * per_tile;
+        const int64_t total = my_tiles * NQ * KB;
+        // (tile, quarter, K-block) of the next item to fetch, advanced without divisions
+        int64_t f_tile = blockIdx.x;
+        int f_nq = 0, f_kb = 0;
         auto fetch = [&](int64_t item, float4* va, float4* vw) {
-            const int64_t tile = blockIdx.x + (item / per_tile) * gridDim.x;
-            const int rem = (int)(item % per_tile);
-            const int nq = rem / KB, kb = rem - nq * KB;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t row = tile * BM + r32 + 32 * i;
+                const int64_t row = f_tile * BM + r32 + 32 * i;
                 va[i] = (item < total && row < p.M)
-                            ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.K + kb * BK) + c)
+                            ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.K + f_kb * BK) + c)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                const int n = nq * 128 + r32 + 32 * i;
-                vw[i] = (item < total) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.ldw + kb * BK) + c)
+                const int n = f_nq * 128 + r32 + 32 * i;
+                vw[i] = (item < total) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.ldw + f_kb * BK) + c)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (++f_kb == KB) { f_kb = 0; if (++f_nq == NQ) { f_nq = 0; f_tile += gridDim.x; } }
         };
         float4 va[4], vw[4], na[4], nw[4];
         fetch(0, va, vw);

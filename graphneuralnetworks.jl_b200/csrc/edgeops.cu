@@ -250,10 +250,16 @@ int edge_dot(gnnb_graph* g, const float* dout, const float* x, const float* cs, 
     return GNNB_OK;
 }
 
+int maxmin_bwd_lean(gnnb_graph* g, const float* w_plan_src, const float* x, const float* dout, const float* out_fwd,
+                    int64_t D, float* dx, cudaStream_t st);   // seglean.cu
 int maxmin_bwd(gnnb_graph* g, const float* w_plan_src, const float* x, const float* dout, const float* out_fwd,
                int64_t D, float* dx, cudaStream_t st) {
     const Csr& c = g->by_src;
     if (c.nrows == 0) return GNNB_OK;
+    {   // rows of 128 / 256 / 512 floats: the work-item kernel (seglean.cu); other widths: one warp per source row
+        const int rc = maxmin_bwd_lean(g, w_plan_src, x, dout, out_fwd, D, dx, st);
+        if (rc != GNNB_EUNSUPPORTED) return rc;
+    }
     maxmin_bwd_kernel<<<nblk((int64_t)c.nrows * 32), 256, 0, st>>>(c.rowptr, c.col, w_plan_src, c.nrows, x, dout,
                                                                    out_fwd, D, dx);
     GNNB_LAUNCHED();

@@ -398,6 +398,111 @@ __global__ void __launch_bounds__(G4<KV>::WARPS * 32, 1) seg_gather4_kernel(cons
     }
 }
 
+// ---- pullback of max / min aggregation on the work-item list of the by-source plan -----------------------------------------
+//   dx[j,:] = sum over out-edges e = (j -> t) of w_e * dout[t,:] .* (x[j,:] * w_e == out_fwd[t,:])      (NNlib's rule: every
+// tied extremum receives the gradient).  Two gathered rows per edge (out_fwd[t], dout[t]) plus the source's own row (an L1
+// hit after its first edge).  The kernel this replaces walked a source's out-edges with ONE warp, serially: a 1 M-edge RMAT
+// hub took 67 ms at N = 2 M / E = 20 M (ncu: 117 GB/s).  Here a hub is cut into 128-edge pieces like every long row.
+struct MaxBwdParams {
+    const int4* __restrict__ items;
+    const int32_t* __restrict__ col;
+    const int32_t* __restrict__ row;
+    const float* __restrict__ w;
+    const float* __restrict__ x;
+    const float* __restrict__ dout;
+    const float* __restrict__ of;
+    float* __restrict__ dx;
+    float* __restrict__ ws;
+    int32_t n_items;
+};
+
+template <int KV, bool HAS_W>
+__global__ void __launch_bounds__(256, 2) maxmin_bwd_lean_kernel(const MaxBwdParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int U = KV == 1 ? 4 : (KV == 2 ? 2 : 1);      // edges in flight per warp (three rows each)
+    constexpr int64_t STRIDE = (int64_t)KV * 128;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (item >= p.n_items) return;
+    const int4 it = __ldg(p.items + item);
+    const int e_end = it.y;
+    const bool partial = __any_sync(FULL, it.z >= 0);
+
+    auto load_lane = [&](int e0, int& c, int& r, float& wv, bool& last) {
+        const int my = e0 + lane;
+        c = 0; r = 0; wv = 1.f; last = false;
+        if (my < e_end) {
+            c = __ldg(p.col + my);
+            r = __ldg(p.row + my);
+            if (HAS_W) wv = __ldg(p.w + my);
+            last = (my + 1 == e_end) || (__ldg(p.row + my + 1) != r);
+        }
+    };
+    float4 acc[KV];
+#pragma unroll
+    for (int i = 0; i < KV; ++i) acc[i] = f4(0.f);
+    int e = it.x;
+    int c_n, r_n;
+    float w_n;
+    bool last_n;
+    load_lane(e, c_n, r_n, w_n, last_n);
+    bool more = true;
+    while (more) {
+        const int c_l = c_n, r_l = r_n;
+        const float w_l = w_n;
+        const unsigned vmask = __ballot_sync(FULL, e + lane < e_end);
+        const unsigned bmask = partial ? 0u : __ballot_sync(FULL, last_n);
+        more = __any_sync(FULL, e + 32 < e_end);
+        if (more) load_lane(e + 32, c_n, r_n, w_n, last_n);
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32 && (vmask >> j0) != 0u; j0 += U) {
+            float4 vo[U][KV], vd[U][KV], vx[U][KV];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int cj = __shfl_sync(FULL, c_l, j0 + u);
+                const int rj = __shfl_sync(FULL, r_l, j0 + u);
+                if ((vmask >> (j0 + u)) & 1u) {
+                    const int64_t to = (int64_t)cj * STRIDE + lane * 4, xo = (int64_t)rj * STRIDE + lane * 4;
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        vo[u][i] = __ldg(reinterpret_cast<const float4*>(p.of + to + i * 128));
+                        vd[u][i] = __ldg(reinterpret_cast<const float4*>(p.dout + to + i * 128));
+                        vx[u][i] = __ldg(reinterpret_cast<const float4*>(p.x + xo + i * 128));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float wv = HAS_W ? __shfl_sync(FULL, w_l, j0 + u) : 1.f;
+                if ((vmask >> (j0 + u)) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        if (__fmul_rn(vx[u][i].x, wv) == vo[u][i].x) acc[i].x += wv * vd[u][i].x;
+                        if (__fmul_rn(vx[u][i].y, wv) == vo[u][i].y) acc[i].y += wv * vd[u][i].y;
+                        if (__fmul_rn(vx[u][i].z, wv) == vo[u][i].z) acc[i].z += wv * vd[u][i].z;
+                        if (__fmul_rn(vx[u][i].w, wv) == vo[u][i].w) acc[i].w += wv * vd[u][i].w;
+                    }
+                }
+                if ((bmask >> (j0 + u)) & 1u) {
+                    const int rj = __shfl_sync(FULL, r_l, j0 + u);
+                    float* o = p.dx + (int64_t)rj * STRIDE + lane * 4;
+#pragma unroll
+                    for (int i = 0; i < KV; ++i) {
+                        *reinterpret_cast<float4*>(o + i * 128) = acc[i];
+                        acc[i] = f4(0.f);
+                    }
+                }
+            }
+        }
+        e += 32;
+    }
+    if (partial) {
+        float* o = p.ws + (int64_t)it.z * STRIDE + lane * 4;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) *reinterpret_cast<float4*>(o + i * 128) = acc[i];
+    }
+}
+
 template <int KV>
 int launch_gather4(const LeanParams& p, int smode, const float* x, int32_t ncols, cudaStream_t st) {
     using C = G4<KV>;
@@ -552,6 +657,41 @@ int seg_reduce_lean(gnnb_graph* g, const Csr& c, const SegArgs& a, float* ws, bo
     else if (a.D == 256) rc = launch_lean1<2>(p, smode, a.w != nullptr, use_halo, agg, st);
     else rc = launch_lean1<4>(p, smode, a.w != nullptr, use_halo, agg, st);
     return rc;
+}
+
+// max / min pullback through the work items of the by-source plan; GNNB_EUNSUPPORTED = not this kernel's shape
+int seg_fixup_sum(const Csr& c, int64_t E, int chunk, int64_t D, float* ws, float* out, cudaStream_t st);   // segreduce.cu
+int maxmin_bwd_lean(gnnb_graph* g, const float* w_plan_src, const float* x, const float* dout, const float* out_fwd,
+                    int64_t D, float* dx, cudaStream_t st) {
+    if (D != 128 && D != 256 && D != 512) return GNNB_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dout) & 15) ||
+        (reinterpret_cast<uintptr_t>(out_fwd) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15))
+        return GNNB_EUNSUPPORTED;
+    const Csr& c = g->by_src;
+    if (g->E == 0) return GNNB_EUNSUPPORTED;
+    GNNB_TRY(ensure_items(g, c, st));
+    if (c.n_empty > 0) {
+        fill_empty_rows_warp_kernel<<<(unsigned)ceil_div((int64_t)c.nrows, 256), 256, 0, st>>>(c.rowptr, c.nrows, dx, D, 0.f);
+        GNNB_LAUNCHED();
+    }
+    MaxBwdParams p;
+    p.items = reinterpret_cast<const int4*>(c.items);
+    p.n_items = c.n_items;
+    p.col = c.col; p.row = c.row; p.w = w_plan_src; p.x = x; p.dout = dout; p.of = out_fwd; p.dx = dx; p.ws = nullptr;
+    if (c.n_long > 0) {
+        GNNB_TRY(ensure_ws(g, (size_t)2 * ceil_div(g->E, g->chunk) * D * sizeof(float)));
+        p.ws = g->ws;
+    }
+    if (p.n_items > 0) {
+        const unsigned blocks = (unsigned)ceil_div(p.n_items, 8);
+        const bool hw = w_plan_src != nullptr;
+        if (D == 128) { if (hw) maxmin_bwd_lean_kernel<1, true><<<blocks, 256, 0, st>>>(p); else maxmin_bwd_lean_kernel<1, false><<<blocks, 256, 0, st>>>(p); }
+        else if (D == 256) { if (hw) maxmin_bwd_lean_kernel<2, true><<<blocks, 256, 0, st>>>(p); else maxmin_bwd_lean_kernel<2, false><<<blocks, 256, 0, st>>>(p); }
+        else { if (hw) maxmin_bwd_lean_kernel<4, true><<<blocks, 256, 0, st>>>(p); else maxmin_bwd_lean_kernel<4, false><<<blocks, 256, 0, st>>>(p); }
+        GNNB_LAUNCHED();
+    }
+    if (c.n_long > 0) GNNB_TRY(seg_fixup_sum(c, g->E, g->chunk, D, p.ws, dx, st));
+    return GNNB_OK;
 }
 
 }  // namespace gnnb

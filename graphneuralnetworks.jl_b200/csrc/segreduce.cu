@@ -358,6 +358,21 @@ int seg_reduce(gnnb_graph* g, const Csr& c, const SegArgs& a, cudaStream_t st) {
     return GNNB_OK;
 }
 
+// the partial slots of the long rows of `c`, added in chunk order into out (plain sums: no scale, no mean)
+int seg_fixup_sum(const Csr& c, int64_t E, int chunk, int64_t D, float* ws, float* out, cudaStream_t st) {
+    if (c.n_long == 0) return GNNB_OK;
+    SegParams p;
+    p.rowptr = c.rowptr; p.col = c.col; p.row = c.row;
+    p.x = nullptr; p.x2 = nullptr; p.split = 0; p.w = nullptr; p.cs = nullptr; p.ct = nullptr; p.out = out;
+    p.D = D; p.E = (int32_t)E; p.nrows = c.nrows; p.chunk = chunk;
+    p.nchunks = (int32_t)ceil_div(E, chunk);
+    p.mean = 0; p.sign = 1.f; p.fill = 0; p.ws = ws;
+    const int64_t threads = (int64_t)c.n_long * ceil_div(D, 4);
+    seg_fixup_kernel<4, false><<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(p, c.long_rows, c.n_long);
+    GNNB_LAUNCHED();
+    return GNNB_OK;
+}
+
 // ---- COO <-> plan order for per-edge values ------------------------------------------------------
 __global__ void permute_kernel(const int32_t* __restrict__ eid, int64_t E, const float* __restrict__ in,
                                int64_t K, float* __restrict__ out, int to_plan) {

@@ -270,7 +270,7 @@ def test_generic_message_functions(graph, oracle, gnn):
 
 # ------------------------------------------------------------------------------------------- pullbacks
 @pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
-@pytest.mark.parametrize("D", [3, 16, 128])
+@pytest.mark.parametrize("D", [3, 16, 128, 256, 512])
 def test_propagate_gradients(graph, oracle, gnn, aggr, D):
     """Zygote/NNlib pullbacks restated through the oracle's gather/scatter."""
     name, s, t, n, g = graph
