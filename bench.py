@@ -80,16 +80,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(name):
-    """dram__bytes_read.sum + dram__bytes_write.sum of launch 1 in a committed profiles/*_ncu_raw.csv (bytes), or None"""
+def ncu_traffic(name, kernel=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of one launch in a committed profiles/*_ncu_raw.csv: the first
+    launch whose kernel name contains `kernel` (launch 1 if None); None if the file or the kernel is missing"""
     import csv
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     try:
-        tot = 0.0
+        tot, col = 0.0, 2
         with open(os.path.join(ROOT, "profiles", name)) as f:
             for row in csv.reader(f):
+                if row and row[0] == "Kernel Name" and kernel is not None:
+                    col = next(i for i, v in enumerate(row) if i >= 2 and kernel in v)
                 if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    tot += float(row[2]) * unit[row[1]]
+                    tot += float(row[col]) * unit[row[1]]
         return tot or None
     except Exception:
         return None
@@ -252,7 +255,8 @@ def dist_parity(args, dg, layer, samples=320, max_deg=20000):
     mark[tg] = True
     ones = torch.ones(min(1 << 26, max(E, 1)), dtype=torch.int32, device=dev)
     ks, kt = [], []
-    for s, t in partition.rmat_chunks(n, E, SEED, dev, 1 << 26):
+    for s1, t1 in partition.rmat_chunks(n, E, SEED, dev, 1 << 26):
+        s, t = s1 - 1, t1 - 1                                # the generated list is 1-based (Julia's convention)
         deg.index_add_(0, t, ones[:t.numel()])
         m = mark[s] | mark[t]
         ks.append(s[m])
@@ -684,8 +688,8 @@ def run_config3(args, torch, gnn, dev):
     alg_b = E2 * (2 * 4 * D + 4 + 8 * H) + 4 * (n + 1) + 2 * 4 * D * n
     peak, peak_src = measured_peaks()
     roof = {"bound": "hbm", "achieved": alg_b / (kb * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_b / (kb * 1e-3) / 1e9 / peak,
-            "traffic": ncu_traffic("r2_gat_bwd_ncu_raw.csv"), "peak_source": peak_src,
-            "kernel": "gnnb::gat_bwd_kernel (attention backward over the CSR-by-source plan: dout and Wx rows gathered per edge)",
+            "traffic": ncu_traffic("r2_gat_lean_ncu_raw.csv", "gat_bwd_lean_kernel"), "peak_source": peak_src,
+            "kernel": "gnnb::gat_bwd_lean_kernel<4> (attention backward over the work items of the CSR-by-source plan: dout and Wx rows gathered per edge)",
             "kernel_ms": {"gat_fwd": kf, "gat_bwd_total": kb}, "algorithmic_bytes_per_launch": alg_b,
             "forward": {"achieved": alg_f / (kf * 1e-3) / 1e9, "frac": alg_f / (kf * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg_f},
             "share_of_step": (kf + kb) / ms}

@@ -139,7 +139,7 @@ class _Shard:
 
 
 def rmat_chunks(num_nodes: int, num_edges: int, seed: int, device, chunk_edges: int = 1 << 26):
-    """the counter-based RMAT list of gnnb_rmat_edges as (src, dst) int64 chunks generated on `device`; the two buffers are
+    """the counter-based RMAT list of gnnb_rmat_edges as (src, dst) int64 chunks (1-based ids) generated on `device`; the two buffers are
     reused, so a chunk is valid until the next one is requested"""
     dev = torch.device(device)
     cap = min(chunk_edges, max(num_edges, 1))
