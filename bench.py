@@ -231,7 +231,10 @@ def dist_parity(args, dg, layer, samples=320, max_deg=20000):
         return out
 
     gen = torch.Generator(device="cpu").manual_seed(99 + rank)
-    idx = torch.unique(torch.cat([torch.arange(min(64, nl)), torch.randint(0, nl, (samples,), generator=gen)])).to(dev)
+    # the deal is by decreasing degree: rows 0.. are the hubs (millions of edges at config 5; the degree cap would drop them
+    # after their edges had been collected), so the high-degree part of the sample starts a little further down
+    head = torch.arange(2048, 2048 + 64) if nl > 8192 else torch.arange(min(64, nl))
+    idx = torch.unique(torch.cat([head, torch.randint(0, nl, (samples,), generator=gen)])).to(dev)
     tg = g_local[idx]
 
     c, cf, cb = dg.gcn_c()
