@@ -96,6 +96,7 @@ struct Params {
     int64_t M;
     int K, Nout, relu, ldw;
     int* err;
+    const float* __restrict__ wimg;  // wide kernel only: W split and swizzled per (quarter, K-block), see tcx::w_image_kernel
 };
 
 __global__ void __launch_bounds__(THREADS, 1) linear_tf32x3_kernel(const Params p) {
@@ -460,9 +461,12 @@ __global__ void dw_reduce_kernel(const float* __restrict__ partial, int nparts, 
 
 // =====================================================================================================================
 // Wide shapes (K and/or Nout above 128: GATConv's 512 -> 8 x 64 projection, config 5's 256 -> 256 layer).  W no longer
-// fits beside the ring, so every stage carries one K-block of BOTH operands: 128 rows of X and 128 rows of W (one column
-// quarter of the output), each split big/small by the loaders.  Item order per CTA: row tile -> output quarter -> K-block;
-// the X tile is re-read from L2 for every quarter (HBM sees it once), W (<= 1 MB) lives in L2.
+// fits beside the ring, so every stage carries one K-block of BOTH operands: 128 rows of X, split big/small by the loader
+// warps, and 128 rows of W (one column quarter of the output), which a small pre-pass has already split and swizzled in
+// global memory so that ONE cp.async.bulk (32 KB, mbarrier complete_tx) drops it into the stage.  Item order per CTA: row
+// tile -> output quarter -> K-block; the X tile is re-read from L2 for every quarter (HBM sees it once), the W image
+// (2 x the size of W, <= 2 MB at 512 x 512) lives in L2.  First version (loaders splitting W as well, one stage of register
+// prefetch): 16.5 ms at 5 M x 512 x 512, tensor pipe 44 % active, no unit saturated: the loaders were the critical path.
 // The big*big products accumulate in one TMEM accumulator and the two cross terms in a second one: the tensor core's
 // accumulator truncates (dw_tf32x3 below measured ~2^-25.7 of the running sum per accumulation), so the chain that carries
 // the full-magnitude sum is kept at K/8 accumulations (64 at K = 512) while the 2K/8 cross-term accumulations act on a sum
@@ -477,6 +481,32 @@ constexpr int SMEM_BIAS_X = SMEM_EPI_X + 4 * 32 * EPI_LD * 4;
 constexpr int MAX_NOUT = 1024;
 constexpr int SMEM_BAR_X = SMEM_BIAS_X + MAX_NOUT * 4;
 constexpr int SMEM_TOTAL_X = SMEM_BAR_X + 128;
+
+// W (Nout x K, row stride ldw) -> the shared-memory images the MMA reads, laid out in global memory block by block:
+// block (quarter nq, K-block kb) = [big 16 KB][small 16 KB], each already in the K-major SWIZZLE_128B order.  One
+// cp.async.bulk of 32 KB then fills the W half of a stage: no loader thread touches W.
+__global__ void w_image_kernel(const float* __restrict__ w, int ldw, int K, int Nout, float* __restrict__ wimg) {
+    const int kv = K >> 2, KB = K / BK;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Nout * kv) return;
+    const int n = idx / kv, c4 = idx - n * kv, kb = c4 >> 3, c = c4 & 7;
+    const int nq = n >> 7, nl = n & 127;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * ldw) + c4);
+    const float4 b = make_float4(tf32_big(v.x), tf32_big(v.y), tf32_big(v.z), tf32_big(v.w));
+    const float4 sm = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+    unsigned char* blk = reinterpret_cast<unsigned char*>(wimg) + (size_t)(nq * KB + kb) * (2 * KBLK_BYTES);
+    const int off = (nl >> 3) * 1024 + (nl & 7) * 128 + ((c ^ (nl & 7)) << 4);
+    *reinterpret_cast<float4*>(blk + off) = b;
+    *reinterpret_cast<float4*>(blk + KBLK_BYTES + off) = sm;
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 
 __global__ void __launch_bounds__(THREADS, 1) linear_wide_tf32x3_kernel(const Params p) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -494,7 +524,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_wide_tf32x3_kernel(const Pa
     float* sbias = reinterpret_cast<float*>(smem + SMEM_BIAS_X);
 
     if (tid == 0) {
-        for (int s = 0; s < XSTAGE; ++s) { bar_init(bar_full + 8 * s, LOADERS); bar_init(bar_empty + 8 * s, 1); }
+        // a stage is full when the 256 loader threads have stored X and the bulk copy of the W block has landed
+        for (int s = 0; s < XSTAGE; ++s) { bar_init(bar_full + 8 * s, LOADERS + 1); bar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { bar_init(bar_tfull + 8 * a, 1); bar_init(bar_tempty + 8 * a, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -509,46 +540,50 @@ __global__ void __launch_bounds__(THREADS, 1) linear_wide_tf32x3_kernel(const Pa
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        // ================= loaders: 4 + 4 float4 per thread and stage, the next stage's already in flight =================
+        // ================= loaders: X only (4 float4 per thread and stage), two stages ahead in registers =================
         const int c = tid & 7, r32 = tid >> 3, rr = r32 & 7;
         const int64_t total = my_tiles * NQ * KB;
         // (tile, quarter, K-block) of the next item to fetch, advanced without divisions
         int64_t f_tile = blockIdx.x;
         int f_nq = 0, f_kb = 0;
-        auto fetch = [&](int64_t item, float4* va, float4* vw) {
+        auto fetch = [&](int64_t item, float4* va) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int64_t row = f_tile * BM + r32 + 32 * i;
                 va[i] = (item < total && row < p.M)
                             ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * p.K + f_kb * BK) + c)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                const int n = f_nq * 128 + r32 + 32 * i;
-                vw[i] = (item < total) ? __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.ldw + f_kb * BK) + c)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (++f_kb == KB) { f_kb = 0; if (++f_nq == NQ) { f_nq = 0; f_tile += gridDim.x; } }
         };
-        float4 va[4], vw[4], na[4], nw[4];
-        fetch(0, va, vw);
+        float4 va[4], na[4], na2[4];
+        fetch(0, va);
+        fetch(1, na);
+        int w_blk = 0;                                          // (quarter, K-block) of the current item: index of its W block
+        const int w_blocks = NQ * KB;
         for (int64_t it = 0; it < total; ++it) {
-            fetch(it + 1, na, nw);
+            fetch(it + 2, na2);
             const int stage = (int)(it % XSTAGE);
             if (!bar_wait(bar_empty + 8 * stage, (uint32_t)(((it / XSTAGE) & 1) ^ 1), p.err)) break;
             unsigned char* sa = smem + stage * XSTAGE_BYTES;
+            if (tid == 0) {
+                bar_expect_tx(bar_full + 8 * stage, 2 * KBLK_BYTES);
+                bulk_g2s(sbase + stage * XSTAGE_BYTES + 2 * KBLK_BYTES,
+                         reinterpret_cast<const unsigned char*>(p.wimg) + (size_t)w_blk * (2 * KBLK_BYTES), 2 * KBLK_BYTES,
+                         bar_full + 8 * stage);
+            }
+            if (++w_blk == w_blocks) w_blk = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int off = ((r32 >> 3) + 4 * i) * 1024 + rr * 128 + ((c ^ rr) << 4);
-                float4 b = make_float4(tf32_big(va[i].x), tf32_big(va[i].y), tf32_big(va[i].z), tf32_big(va[i].w));
+                const float4 b = make_float4(tf32_big(va[i].x), tf32_big(va[i].y), tf32_big(va[i].z), tf32_big(va[i].w));
                 *reinterpret_cast<float4*>(sa + off) = b;
                 *reinterpret_cast<float4*>(sa + KBLK_BYTES + off) = make_float4(va[i].x - b.x, va[i].y - b.y, va[i].z - b.z, va[i].w - b.w);
-                b = make_float4(tf32_big(vw[i].x), tf32_big(vw[i].y), tf32_big(vw[i].z), tf32_big(vw[i].w));
-                *reinterpret_cast<float4*>(sa + 2 * KBLK_BYTES + off) = b;
-                *reinterpret_cast<float4*>(sa + 3 * KBLK_BYTES + off) = make_float4(vw[i].x - b.x, vw[i].y - b.y, vw[i].z - b.z, vw[i].w - b.w);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             bar_arrive(bar_full + 8 * stage);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { va[i] = na[i]; vw[i] = nw[i]; }
+            for (int i = 0; i < 4; ++i) { va[i] = na[i]; na[i] = na2[i]; }
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer: M = 128, N = 128 per instruction =================
@@ -676,7 +711,20 @@ int linear_tf32x3_ex(const float* x, const float* W, int64_t ldw, const float* b
     }
     tc::Params p;
     p.x = x; p.w = W; p.bias = bias; p.addend = addend; p.y = y; p.M = M; p.K = (int)K; p.Nout = (int)Nout; p.relu = relu;
-    p.ldw = (int)ldw; p.err = g_tc_err;
+    p.ldw = (int)ldw; p.err = g_tc_err; p.wimg = nullptr;
+    if (wide) {
+        // the split, swizzled image of W (2 x its size), rebuilt per call: W changes between training steps
+        static float* wimg = nullptr; static size_t wimg_elems = 0;
+        const size_t need = (size_t)2 * K * Nout;
+        if (wimg_elems < need) {
+            if (wimg) { cudaDeviceSynchronize(); cudaFree(wimg); wimg = nullptr; wimg_elems = 0; }
+            GNNB_CUDA(cudaMalloc(&wimg, sizeof(float) * need));
+            wimg_elems = need;
+        }
+        tcx::w_image_kernel<<<(unsigned)ceil_div(Nout * (K / 4), 256), 256, 0, st>>>(W, (int)ldw, (int)K, (int)Nout, wimg);
+        GNNB_LAUNCHED();
+        p.wimg = wimg;
+    }
     const int64_t ntiles = ceil_div(M, tc::BM);
     const unsigned grid = (unsigned)(ntiles < nsm ? ntiles : nsm);
     if (wide) tcx::linear_wide_tf32x3_kernel<<<grid, tc::THREADS, tcx::SMEM_TOTAL_X, st>>>(p);

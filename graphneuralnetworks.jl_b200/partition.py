@@ -172,6 +172,7 @@ class DistGraph:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.timing = {}                                     # build phases, ms (this rank)
         self.device = torch.device(device) if device is not None else s.device
         self.num_nodes = int(num_nodes)
         self.ownership = ownership
@@ -193,6 +194,7 @@ class DistGraph:
                 raise ValueError("ownership='balanced' needs the chunks twice: pass a list or a callable that returns an iterator")
             W, N = self.world, self.num_nodes
             it = chunks() if callable(chunks) else chunks
+            t_own = time.perf_counter()
             if self.device.type == "cuda":                   # degree histogram + stable sort + deal, on the device
                 cost = torch.zeros(N, dtype=torch.int32, device=self.device)
                 self._relabel = torch.empty(N, dtype=torch.int32, device=self.device)
@@ -216,6 +218,9 @@ class DistGraph:
                 self._order = torch.empty(N, dtype=torch.int64, device=self.device)      # position -> node
                 self._order[self._relabel.long()] = pos
                 del by_degree, pos, r, j, o
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            self.timing["ownership_ms"] = (time.perf_counter() - t_own) * 1e3
         if callable(chunks):
             chunks = chunks()
         self.first = ownership_first(self.num_nodes, self.world, ownership, bounds)
@@ -224,6 +229,7 @@ class DistGraph:
         self.n_local = self.hi - self.lo
         if self.device.type == "cuda":
             self.fwd, self.bwd = self._build_native(chunks)
+            torch.cuda.synchronize(self.device)
         else:
             self.fwd, self.bwd = self._build_torch(chunks)
 
@@ -250,6 +256,7 @@ class DistGraph:
         b = C.c_void_p()
         bounds_arr = (C.c_int64 * (world + 1))(*self.first) if self.ownership == "contiguous" else None
         shards = []
+        t_sh = time.perf_counter()
         with torch.cuda.device(dev):
             st = _stream(dev)
             _lib.check(lib.gnnb_shard_builder_create(C.byref(b), self.num_nodes, world, self.rank,
@@ -271,10 +278,15 @@ class DistGraph:
                     shards.append((h, nl.value, nh.value, ne.value, list(rc), halo_local))
             finally:
                 lib.gnnb_shard_builder_destroy(b)
+        torch.cuda.synchronize(dev)
+        self.timing["shards_ms"] = (time.perf_counter() - t_sh) * 1e3
+        t_ex = time.perf_counter()
         out = []
         for h, nl, nh, ne, rc, halo_local in shards:
             send_idx, send_counts = exchange_requests(halo_local, rc, self.group)
             out.append(_Shard(nl, nh, rc, ne, send_idx, send_counts, _Plan(h.value, dev)))
+        torch.cuda.synchronize(dev)
+        self.timing["request_exchange_ms"] = (time.perf_counter() - t_ex) * 1e3
         return out
 
     def _plans(self, d):
@@ -505,7 +517,19 @@ def dist_gcn_conv(l, dg: DistGraph, x_local: torch.Tensor) -> torch.Tensor:
 def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_leg=None, parity=None):
     import gnnb200 as gnn
     n, E, D = args.nodes, args.edges, args.dim
+    # NCCL opens its peer-to-peer connections lazily, on the first all-to-all (seconds at 8 ranks): communicator set-up is
+    # not shard construction, so it is paid (and reported) before the plan timer starts
     torch.cuda.synchronize()
+    tc0 = time.perf_counter()
+    warm = torch.zeros(world * 4, device=dev)
+    warm_out = torch.empty_like(warm)
+    dist.all_to_all_single(warm_out, warm)
+    dist.all_reduce(warm)
+    dist.all_gather([torch.empty_like(warm) for _ in range(world)], warm)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_comm = time.perf_counter() - tc0
+    del warm, warm_out
     t0 = time.perf_counter()
     # every rank generates the counter-based edge list chunk by chunk and keeps its shard (csrc/shard.cu); 'balanced'
     # ownership deals the nodes to the ranks by decreasing degree (one extra pass over the generated chunks)
@@ -664,7 +688,8 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_
                        "parallelism": f"node-partition x{world}, {ownership} ownership, shards built on the device from generated chunks",
                        "halo_exchange": os.environ.get("GNNB_HALO", "push") + (" (one kernel writes rows into peer halo buffers over NVLink, CUDA IPC)" if os.environ.get("GNNB_HALO", "push") == "push" else " (pack kernel + NCCL all_to_all_single)"),
                        "l2": "per-GPU features and halo buffers are far larger than the 126 MB L2",
-                       "plan_build_ms": t_plan * 1e3, "chunk_edges": 128,
+                       "plan_build_ms": t_plan * 1e3, "plan_build_phases_ms_rank0": {k: round(v, 1) for k, v in dg.timing.items()},
+                       "nccl_connection_setup_ms": t_comm * 1e3, "chunk_edges": 128,
                        "per_rank": {"kernel_ms": allst[:, 0].tolist(), "halo_exchange_ms": allst[:, 1].tolist(),
                                     "shard_edges": allst[:, 2].tolist(), "n_local": allst[:, 3].tolist(),
                                     "halo_rows_fwd": allst[:, 4].tolist(), "halo_rows_bwd": allst[:, 5].tolist()}},
