@@ -14,3 +14,6 @@ fn $B/segbulk.o 'seg_reduce_bulk_kernelILi1ELi2ELi3ELb0E' | hist > $O/r2_seg_red
 fn $B/dense_tc.o 'linear_tf32x3_kernel' | hist > $O/r2_linear_tf32x3_kernel.hist
 fn $B/dense_tc.o 'dw_tf32x3_kernel' | hist > $O/r2_dw_tf32x3_kernel.hist
 ls -la $O
+fn $B/dense_tc.o 'linear_wide_tf32x3_kernel' | hist > $O/r2_linear_wide_tf32x3_kernel.hist
+fn $B/seglean.o 'maxmin_bwd_lean_kernelILi1ELb0E' | hist > $O/r2_maxmin_bwd_lean_kernel_D128.hist
+ls -la $O
