@@ -536,8 +536,12 @@ def bench_multi(args, world, rank, dev, seed, ClockSampler, measured_peaks, cpu_
     ownership = os.environ.get("GNNB_OWNERSHIP", "balanced")
     dg = DistGraph.from_rmat(n, E, seed, device=dev, add_self_loops=True, ownership=ownership,
                              chunk_edges=int(os.environ.get("GNNB_CHUNK_EDGES", str(1 << 26))))
+    torch.cuda.synchronize()
+    dg.timing["constructor_total_ms"] = (time.perf_counter() - t0) * 1e3
+    tg0 = time.perf_counter()
     dg.gcn_c()
     torch.cuda.synchronize()
+    dg.timing["gcn_norm_and_its_halo_ms"] = (time.perf_counter() - tg0) * 1e3
     t_plan = time.perf_counter() - t0
     torch.cuda.empty_cache()
 
