@@ -129,3 +129,41 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     assert subprocess.check_output(cmd, text=True, timeout=300, env=env).strip() == ""
+
+
+def _bench_module():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_ncu_extracts():
+    """roofline.traffic must come from the committed CSV of the CURRENT kernel, selected by name — not a literal"""
+    b = _bench_module()
+    lean = b.ncu_traffic("r2_seg_lean_v0_ncu_raw.csv")
+    assert lean is not None and 35e9 < lean < 45e9                        # config 2: 39.2 GB per launch
+    fwd = b.ncu_traffic("r2_gat_lean_ncu_raw.csv", "gat_fwd_lean_kernel")
+    bwd = b.ncu_traffic("r2_gat_lean_ncu_raw.csv", "gat_bwd_lean_kernel")
+    assert fwd is not None and bwd is not None and bwd > fwd > 50e9       # config 3: 94.7 / 126.4 GB
+    assert b.ncu_traffic("r2_gat_lean_ncu_raw.csv", "no_such_kernel") is None
+    assert b.ncu_traffic("no_such_file.csv") is None
+    assert b.ncu_traffic("r2_seg_lean_mean_c4_ncu_raw.csv") is not None   # config 4's mean kernel
+
+
+def test_bench_argument_surface():
+    """the flags the driver and the scripts rely on"""
+    import sys
+    b = _bench_module()
+    old = sys.argv
+    try:
+        sys.argv = ["bench.py", "--gpus", "8", "--steps", "4", "--warmup", "3", "--config", "5", "--no-parity", "--no-cpu", "--no-e2e"]
+        a = b.parse()
+    finally:
+        sys.argv = old
+    assert (a.gpus, a.steps, a.warmup, a.config) == (8, 4, 3, 5)
+    assert a.no_parity and a.no_cpu and a.no_e2e and a.impl != "reference"
+    assert (a.nodes, a.edges, a.dim) == (100_000_000, 1_000_000_000, 256)     # config 5 = BASELINE configs[4]
