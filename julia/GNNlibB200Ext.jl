@@ -198,6 +198,37 @@ function ChainRulesCore.rrule(::typeof(fused_linear), W, x, b, relu::Bool)
     return y, fused_linear_pullback
 end
 
+# ---- closing line of a layer that ends in an aggregation: σ.(x .+ b) (gnnb_bias_act, gnnb_bias_act_bwd) ---------------
+# one pass forward, one pass backward (mask product + deterministic bias gradient) instead of four broadcasts
+function bias_act(x::CuMatrix{Float32}, b::Union{Nothing, CuVector{Float32}}, relu::Bool)
+    D, N = size(x)
+    y = similar(x)
+    check(ccall((:gnnb_bias_act, LIB), Cint,
+                (CuPtr{Float32}, CuPtr{Float32}, Cint, Int64, Int64, CuPtr{Float32}, Ptr{Cvoid}),
+                x, cuptr(b), relu, N, D, y, stream()))
+    return y
+end
+
+function ChainRulesCore.rrule(::typeof(bias_act), x, b, relu::Bool)
+    y = bias_act(x, b, relu)
+    function bias_act_pullback(Δ)
+        dy = CuArray{Float32}(unthunk(Δ))
+        D, N = size(dy)
+        dpre = relu ? similar(dy) : dy
+        db = b === nothing ? nothing : similar(b)
+        (relu || db !== nothing) &&
+            check(ccall((:gnnb_bias_act_bwd, LIB), Cint,
+                        (CuPtr{Float32}, CuPtr{Float32}, Cint, Int64, Int64, CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
+                        dy, relu ? pointer(y) : CU_NULL, relu, N, D, relu ? pointer(dpre) : CU_NULL, cuptr(db), stream()))
+        return NoTangent(), dpre, db === nothing ? NoTangent() : db, NoTangent()
+    end
+    return y, bias_act_pullback
+end
+
+closing(l, y::CuMatrix{Float32}) =
+    (fusable_σ(l.σ) && size(y, 1) % 4 == 0 && size(y, 1) <= 1024 && (l.bias === false || l.bias isa CuVector{Float32})) ?
+    bias_act(y, l.bias === false ? nothing : l.bias, isrelu(l.σ)) : l.σ.(y .+ l.bias)
+
 dense(l, W, x, with_bias_act::Bool) = begin
     b = (with_bias_act && l.bias isa CuVector{Float32}) ? l.bias : nothing
     σ = with_bias_act ? l.σ : identity
@@ -306,7 +337,7 @@ function GNNlib.gat_conv(l, g::GNNGraph{<:COO_T}, x::CuMatrix{Float32}, e::Nothi
     y = gat_aggregate(p, Wx, el, er, Float32(l.negative_slope))
     l.concat || (y = mean(y, dims = 2))
     y = reshape(y, :, size(y, 3))
-    return l.σ.(y .+ l.bias)
+    return closing(l, y)                                                 # conv.jl:149, one pass
 end
 
 # ---- sage_conv fast path (GNNlib/src/layers/conv.jl:277-283; caller GraphNeuralNetworks/src/layers/conv.jl:787) ------
