@@ -201,7 +201,9 @@ int gnnb_gat_logit_terms_bwd(const float* Wx, const float* a, const float* del, 
 /* ------------------------------------------------------- dense layer part
  * replaces: l.σ.(weight * x .+ l.bias) of the conv layers (GNNlib/src/layers/conv.jl:39,69-71; :281) and its pullback.
  * Din, Dout <= 128: hand-written tcgen05 kernels (csrc/dense_tc.cu: 3xTF32 split, TMEM accumulators, bias/relu epilogue
- * written as whole row segments); every other shape: a library GEMM like the reference's, issued through cuBLASLt 12.9
+ * written as whole row segments, W resident in shared memory); Din % 32 == 0 <= 2048 and Dout % 128 == 0 <= 1024 with at
+ * least 2048 nodes: the wide tcgen05 kernel of the same file (both operands streamed, W through cp.async.bulk; forward and
+ * dx); every other shape: a library GEMM like the reference's, issued through cuBLASLt 12.9
  * with the fp32-emulated compute type (bf16 x9, fp32 accumulate; SIMT sgemm if unavailable), bias (+relu) in the epilogue.  x (Din,N), W (Dout,Din) row-major as the layer stores it, bias NULL or Dout floats, y (Dout,N).
  * relu: 0 = identity, 1 = relu. */
 int gnnb_linear(const float* x, const float* W, const float* bias, int relu, int64_t N, int64_t Din,
@@ -230,9 +232,9 @@ int gnnb_bias_act_bwd(const float* dy, const float* y, int relu, int64_t N, int6
 /* 1 (default) = try the fp32-emulated tensor-core GEMM; 0 = force the SIMT sgemm.  *_active: -1 not yet used,
  * 0 unavailable / off, 1 in use. */
 int gnnb_dense_set_emulation(int on);
-/* The hand-written tcgen05 kernel (csrc/dense_tc.cu: 3xTF32 split, TMEM accumulators, bias/relu epilogue) serves
- * Din, Dout <= 128 (Din % 32 == 0, Dout % 16 == 0) for gnnb_linear and the dx part of gnnb_linear_bwd; 0 switches it
- * off (cuBLASLt everywhere).  gnnb_dense_tc_error() != 0 means one of its bounded pipeline waits expired. */
+/* The hand-written tcgen05 kernels (csrc/dense_tc.cu: 3xTF32 split, TMEM accumulators, bias/relu epilogue) serve
+ * Din, Dout <= 128 (Din % 32 == 0, Dout % 16 == 0) and the wide shapes named above for gnnb_linear and the dx part of
+ * gnnb_linear_bwd (dW: Dout == 128 only); 0 switches them off (cuBLASLt everywhere).  gnnb_dense_tc_error() != 0 means one of its bounded pipeline waits expired. */
 int gnnb_dense_set_tensor_core_kernel(int on);
 int gnnb_dense_tc_error(void);
 int gnnb_dense_emulation_active(void);
